@@ -1,0 +1,192 @@
+/*
+ * plonky2_b200.h -- C ABI of the B200-native polynomial-commitment library (libplonky2_b200.so).
+ *
+ * This is the drop-in boundary for the path the reference accelerates through its `plonky2_cuda` crate:
+ *   reference FFI declarations   cuda/src/lib.rs:52-145
+ *   reference definitions        cuda/plonky2_gpu.cu:57-785
+ *   reference callers            plonky2/src/fri/oracle.rs:279-545 (from_values_with_gpu), :547-700
+ *                                (from_coeffs_with_gpu), plonky2/src/plonk/prover.rs:535-568 (my_prove)
+ *
+ * Two layers are exported:
+ *   1. A generic API (`p2b_*`): 64-bit sizes, explicit host/device flags, int status codes with
+ *      p2b_last_error().  It implements PolynomialBatch::from_values / from_coeffs
+ *      (plonky2/src/fri/oracle.rs:709-731, 911-977), MerkleTree::new / prove
+ *      (plonky2/src/hash/merkle_tree.rs:283-319, 392-440), get_lde_values (oracle.rs:1007-1018) and
+ *      compute_quotient_polys (plonky2/src/plonk/prover.rs:790-1034) for any (rows, columns, rate_bits,
+ *      cap_height, gate set).
+ *   2. The reference's own six symbols (`init`, `ifft`, `build_merkle_tree`, `merkle_tree_from_values`,
+ *      `merkle_tree_from_coeffs`, `compute_quotient_polys`) plus `transpose`/`fft_blinding`, with the
+ *      reference's exact signatures, in-place device-memory layout and by-value error struct, so
+ *      cuda/src/lib.rs links against this library unchanged.  See INTEGRATION.md.
+ *
+ * All data are Goldilocks field elements stored as little-endian u64.  Everything the library returns is
+ * canonical (< p).  There is no CPU fallback: every entry fails with P2B_ERR_CUDA if no sm_100 device is
+ * usable.
+ */
+#ifndef PLONKY2_B200_H
+#define PLONKY2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------------------------------------------
+ * Status codes
+ * ------------------------------------------------------------------------------------------------- */
+enum {
+  P2B_OK = 0,
+  P2B_ERR_INVALID = 1, /* bad argument (e.g. cap_height > log2(leaves), merkle_tree.rs:285-290)          */
+  P2B_ERR_CUDA = 2,    /* a CUDA call or kernel launch failed; p2b_last_error() has the CUDA string     */
+  P2B_ERR_OOM = 3,     /* device allocation failed                                                      */
+  P2B_ERR_UNSUPPORTED = 4
+};
+
+typedef struct p2b_ctx p2b_ctx;     /* per-device context: streams, twiddle tables, workspace           */
+typedef struct p2b_batch p2b_batch; /* a committed PolynomialBatch resident on the device               */
+
+/* Thread-local message of the last failing call ("" if none). */
+const char* p2b_last_error(void);
+/* Library / build identification, e.g. "plonky2_b200 0.1 sm_100a". */
+const char* p2b_version(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Context.  Replaces the reference's externally constructed `CudaInvContext`
+ * (plonky2/src/fri/oracle.rs:75-109: streams + root tables + shift powers + one big cache buffer).
+ * ------------------------------------------------------------------------------------------------- */
+int p2b_ctx_create(int device /* -1 = current */, p2b_ctx** out);
+void p2b_ctx_destroy(p2b_ctx* ctx);
+/* The CUDA stream (cudaStream_t) the context launches on; callers may enqueue their own copies on it. */
+void* p2b_ctx_stream(p2b_ctx* ctx);
+int p2b_ctx_synchronize(p2b_ctx* ctx);
+/* Kernels launched by this context since creation (for bench.py's gpu_launches). */
+uint64_t p2b_ctx_launch_count(const p2b_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------------
+ * PolynomialBatch::from_values / from_coeffs
+ *   values / coeffs : column-major [P][n], n = 2^n_log (one polynomial after another, as the reference
+ *                     flattens them: fri/oracle.rs:352-362).  Host or device pointer per `on_host`.
+ *   salt            : NULL (blinding = false) or column-major [4][n << rate_bits] blinding columns in
+ *                     LDE-domain order (the reference draws them with F::rand_vec, oracle.rs:998-1002;
+ *                     the caller supplies them so results are reproducible).  SALT_SIZE = 4, oracle.rs:41.
+ * The batch keeps, on the device: coefficients [P][n]; leaves row-major [N][P + salt] in the reference's
+ * bit-reversed leaf order; digests (2*(N - 2^cap_height) x 4, reference layout); cap (2^cap_height x 4).
+ * ------------------------------------------------------------------------------------------------- */
+#define P2B_SALT_SIZE 4
+
+int p2b_commit_from_values(p2b_ctx* ctx, const uint64_t* values, int values_on_host, uint32_t n_log, uint64_t P,
+                           uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, int salt_on_host,
+                           p2b_batch** out);
+int p2b_commit_from_coeffs(p2b_ctx* ctx, const uint64_t* coeffs, int coeffs_on_host, uint32_t n_log, uint64_t P,
+                           uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, int salt_on_host,
+                           p2b_batch** out);
+void p2b_batch_destroy(p2b_batch* b);
+
+typedef struct {
+  uint32_t degree_log; /* n_log                                    (PolynomialBatch.degree_log) */
+  uint32_t rate_bits;
+  uint32_t cap_height;
+  uint32_t salt_size;  /* 0 or 4                                   (blinding)                   */
+  uint64_t num_polys;  /* P                                                                     */
+  uint64_t num_leaves; /* N = n << rate_bits                                                    */
+  uint64_t leaf_len;   /* P + salt_size                                                         */
+  uint64_t num_digests;/* 2 * (N - 2^cap_height)                                                */
+} p2b_batch_info;
+int p2b_batch_get_info(const p2b_batch* b, p2b_batch_info* out);
+
+/* Device pointers of the resident arrays (any out pointer may be NULL). */
+int p2b_batch_device_ptrs(const p2b_batch* b, uint64_t** coeffs, uint64_t** leaves, uint64_t** digests,
+                          uint64_t** cap);
+
+/* Copies to HOST buffers (synchronous on the context stream). */
+int p2b_batch_get_coeffs(const p2b_batch* b, uint64_t* out /* [P][n] */);
+int p2b_batch_get_cap(const p2b_batch* b, uint64_t* out /* [2^cap_height][4] */);
+int p2b_batch_get_digests(const p2b_batch* b, uint64_t* out /* [num_digests][4] */);
+int p2b_batch_get_leaves(const p2b_batch* b, uint64_t first_leaf, uint64_t count, uint64_t* out /* [count][leaf_len] */);
+/* get_lde_values(index, step) (fri/oracle.rs:1007-1018): the row at reverse_bits(index*step), salt stripped. */
+int p2b_batch_get_lde_values(const p2b_batch* b, uint64_t index, uint64_t step, uint64_t* out /* [P] */);
+/* MerkleTree::prove (merkle_tree.rs:392-440): (log2 N - cap_height) sibling hashes for each leaf index. */
+int p2b_batch_prove(const p2b_batch* b, const uint64_t* leaf_indices, uint64_t count,
+                    uint64_t* siblings_out /* [count][log2 N - cap_height][4] */);
+/* Rows + proofs for FRI query rounds in one gather (fri/prover.rs:187-216 reads them row by row). */
+int p2b_batch_open_rows(const p2b_batch* b, const uint64_t* leaf_indices, uint64_t count,
+                        uint64_t* rows_out /* [count][leaf_len] */, uint64_t* siblings_out /* or NULL */);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Building blocks (device pointers unless stated).  Each mirrors one reference function.
+ * ------------------------------------------------------------------------------------------------- */
+/* values.into_par_iter().map(|v| v.ifft())  (fri/oracle.rs:717-721, field/src/fft.rs:73-103).
+ * d_src / d_dst column-major [P][n]; may alias. */
+int p2b_ifft_batch(p2b_ctx* ctx, const uint64_t* d_src, uint64_t* d_dst, uint32_t n_log, uint64_t P);
+/* lde_values + transpose + reverse_index_bits (fri/oracle.rs:979-1004, 942-952): d_coeffs [P][n] ->
+ * d_leaves rows [N][row_stride] (columns col0 .. col0+P of each row). */
+int p2b_lde_leaves(p2b_ctx* ctx, const uint64_t* d_coeffs, uint32_t n_log, uint64_t P, uint32_t rate_bits,
+                   uint64_t* d_leaves, uint64_t row_stride, uint64_t col0);
+/* MerkleTree::new on leaf rows (merkle_tree.rs:283-319).  Element (row, col) of the leaves is at
+ * d_leaves[row * row_stride + col * col_stride]. */
+int p2b_merkle_tree(p2b_ctx* ctx, const uint64_t* d_leaves, uint64_t num_leaves, uint64_t leaf_len,
+                    uint64_t row_stride, uint64_t col_stride, uint32_t cap_height, uint64_t* d_digests,
+                    uint64_t* d_cap);
+/* F::poseidon on `count` independent 12-word states, in place (hash/poseidon.rs:590-606). */
+int p2b_poseidon_permute(p2b_ctx* ctx, uint64_t* d_states, uint64_t count);
+/* Element-wise field ops for the parity tests: op 0 add, 1 sub, 2 mul; out[i] = a[i] op b[i] (canonical). */
+int p2b_field_op(p2b_ctx* ctx, int op, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, uint64_t count);
+/* Deterministic synthetic input: out[i] = splitmix64(seed, first_index + i) rejected >= p. */
+int p2b_fill_synthetic(p2b_ctx* ctx, uint64_t* d_out, uint64_t count, uint64_t seed, uint64_t first_index);
+
+/* Device memory helpers so that non-CUDA hosts (ctypes, Rust FFI) need no second allocator. */
+int p2b_malloc(p2b_ctx* ctx, uint64_t bytes, void** out);
+int p2b_free(p2b_ctx* ctx, void* ptr);
+int p2b_malloc_host(uint64_t bytes, void** out); /* pinned */
+int p2b_free_host(void* ptr);
+int p2b_memcpy_h2d(p2b_ctx* ctx, void* d_dst, const void* h_src, uint64_t bytes);
+int p2b_memcpy_d2h(p2b_ctx* ctx, void* h_dst, const void* d_src, uint64_t bytes);
+/* Time on the context's stream: event pair helpers returning milliseconds (bench.py uses these so the
+ * timing is taken on the stream the kernels are launched on). */
+int p2b_timer_start(p2b_ctx* ctx);
+int p2b_timer_stop_ms(p2b_ctx* ctx, float* ms_out);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Reference-compatible symbols (cuda/src/lib.rs:52-145).  Same names, argument order, in-place device
+ * layout and error convention (struct returned by value: CUDA error code + strdup'd message or NULL, which
+ * the Rust side frees, lib.rs:20-51).  `ctx` points at {cudaStream_t stream; cudaStream_t stream2;}
+ * (cuda/plonky2_gpu.cu:4-7).  root tables / shift powers / n_inv arguments are accepted and ignored: the
+ * library owns its twiddle tables.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int code;
+  char* message;
+} p2b_rust_error; /* == cuda::Error (lib.rs:20-25) == RustError (plonky2_gpu.cu:19-31) */
+
+typedef struct {
+  const void* ptr;
+  int len;
+} p2b_data_slice; /* == DataSlice (lib.rs:52-56) */
+
+#ifndef P2B_NO_COMPAT_SYMBOLS
+void init(void); /* lib.rs:59 (declared there, never defined by the reference) */
+p2b_rust_error ifft(uint64_t* d_values_flatten, int poly_num, int values_num_per_poly, int log_len,
+                    const uint64_t* d_root_table, const uint64_t* p_inv, void* ctx); /* lib.rs:61-69 */
+p2b_rust_error build_merkle_tree(uint64_t* d_ext_values_flatten, int poly_num, int values_num_per_poly,
+                                 int log_len, int rate_bits, int salt_size, int cap_height,
+                                 int pad_extvalues_len, void* ctx); /* lib.rs:71-81 */
+p2b_rust_error merkle_tree_from_values(uint64_t* d_values_flatten, uint64_t* d_ext_values_flatten, int poly_num,
+                                       int values_num_per_poly, int log_len, const uint64_t* d_root_table,
+                                       const uint64_t* d_root_table2, const uint64_t* d_shift_powers,
+                                       const uint64_t* p_inv, int rate_bits, int salt_size, int cap_height,
+                                       int pad_extvalues_len, void* ctx); /* lib.rs:83-98 */
+p2b_rust_error merkle_tree_from_coeffs(uint64_t* d_values_flatten, uint64_t* d_ext_values_flatten, int poly_num,
+                                       int values_num_per_poly, int log_len, const uint64_t* d_root_table,
+                                       const uint64_t* d_root_table2, const uint64_t* d_shift_powers,
+                                       int rate_bits, int salt_size, int cap_height, int pad_extvalues_len,
+                                       void* ctx); /* lib.rs:100-114 */
+p2b_rust_error transpose(uint64_t* d_ext_values_flatten, int poly_num, int values_num_per_poly, int rate_bits,
+                         int salt_size, int pad_extvalues_len, void* ctx); /* plonky2_gpu.cu:192-215 */
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLONKY2_B200_H */

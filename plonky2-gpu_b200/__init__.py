@@ -1,0 +1,386 @@
+"""plonky2_gpu_b200 -- host-side Python binding of libplonky2_b200.so (ctypes over the C ABI in
+include/plonky2_b200.h).  Used by tests/, bench.py and __graft_entry__.py; mirrors the reference's
+PolynomialBatch / MerkleTree interface (plonky2/src/fri/oracle.rs:112-120, 709-1018;
+plonky2/src/hash/merkle_tree.rs:41-66, 383-440) so the parity tests read like the reference's own.
+
+There is NO CPU fallback: loading fails loudly if the CUDA library is missing, and every call fails if no
+sm_100 device is present.
+"""
+import ctypes as C
+import importlib.util
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libplonky2_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "plonky2_b200.h")
+ORDER = 0xFFFFFFFF00000001
+SALT_SIZE = 4
+
+P2B_OK, P2B_ERR_INVALID, P2B_ERR_CUDA, P2B_ERR_OOM, P2B_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
+
+
+class P2BError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("p2b error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _load_build_module():
+    spec = importlib.util.spec_from_file_location("p2b_build", os.path.join(_HERE, "build.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    return _load_build_module().build(force=force, verbose=verbose)
+
+
+class BatchInfo(C.Structure):
+    _fields_ = [("degree_log", C.c_uint32), ("rate_bits", C.c_uint32), ("cap_height", C.c_uint32),
+                ("salt_size", C.c_uint32), ("num_polys", C.c_uint64), ("num_leaves", C.c_uint64),
+                ("leaf_len", C.c_uint64), ("num_digests", C.c_uint64)]
+
+
+class RustError(C.Structure):
+    _fields_ = [("code", C.c_int), ("message", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library (raises if it has not been built: no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: run `python plonky2-gpu_b200/build.py` (there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u64, u32, i = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+    sigs = {
+        "p2b_last_error": (C.c_char_p, []),
+        "p2b_version": (C.c_char_p, []),
+        "p2b_ctx_create": (i, [i, C.POINTER(vp)]),
+        "p2b_ctx_destroy": (None, [vp]),
+        "p2b_ctx_stream": (vp, [vp]),
+        "p2b_ctx_synchronize": (i, [vp]),
+        "p2b_ctx_launch_count": (u64, [vp]),
+        "p2b_commit_from_values": (i, [vp, vp, i, u32, u64, u32, u32, vp, i, C.POINTER(vp)]),
+        "p2b_commit_from_coeffs": (i, [vp, vp, i, u32, u64, u32, u32, vp, i, C.POINTER(vp)]),
+        "p2b_batch_destroy": (None, [vp]),
+        "p2b_batch_get_info": (i, [vp, C.POINTER(BatchInfo)]),
+        "p2b_batch_device_ptrs": (i, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+        "p2b_batch_get_coeffs": (i, [vp, vp]),
+        "p2b_batch_get_cap": (i, [vp, vp]),
+        "p2b_batch_get_digests": (i, [vp, vp]),
+        "p2b_batch_get_leaves": (i, [vp, u64, u64, vp]),
+        "p2b_batch_get_lde_values": (i, [vp, u64, u64, vp]),
+        "p2b_batch_prove": (i, [vp, vp, u64, vp]),
+        "p2b_batch_open_rows": (i, [vp, vp, u64, vp, vp]),
+        "p2b_ifft_batch": (i, [vp, vp, vp, u32, u64]),
+        "p2b_lde_leaves": (i, [vp, vp, u32, u64, u32, vp, u64, u64]),
+        "p2b_merkle_tree": (i, [vp, vp, u64, u64, u64, u64, u32, vp, vp]),
+        "p2b_poseidon_permute": (i, [vp, vp, u64]),
+        "p2b_field_op": (i, [vp, i, vp, vp, vp, u64]),
+        "p2b_fill_synthetic": (i, [vp, vp, u64, u64, u64]),
+        "p2b_malloc": (i, [vp, u64, C.POINTER(vp)]),
+        "p2b_free": (i, [vp, vp]),
+        "p2b_malloc_host": (i, [u64, C.POINTER(vp)]),
+        "p2b_free_host": (i, [vp]),
+        "p2b_memcpy_h2d": (i, [vp, vp, vp, u64]),
+        "p2b_memcpy_d2h": (i, [vp, vp, vp, u64]),
+        "p2b_timer_start": (i, [vp]),
+        "p2b_timer_stop_ms": (i, [vp, C.POINTER(C.c_float)]),
+        # reference-compatible symbols (cuda/src/lib.rs:52-145)
+        "init": (None, []),
+        "ifft": (RustError, [vp, i, i, i, vp, vp, vp]),
+        "build_merkle_tree": (RustError, [vp, i, i, i, i, i, i, i, vp]),
+        "merkle_tree_from_values": (RustError, [vp, vp, i, i, i, vp, vp, vp, vp, i, i, i, i, vp]),
+        "merkle_tree_from_coeffs": (RustError, [vp, vp, i, i, i, vp, vp, vp, i, i, i, i, vp]),
+        "transpose": (RustError, [vp, i, i, i, i, i, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != P2B_OK:
+        raise P2BError(rc, lib().p2b_last_error().decode())
+
+
+def _np(x):
+    return np.ascontiguousarray(x, dtype=np.uint64)
+
+
+class DeviceBuffer:
+    """A device allocation of u64 elements owned by a Context."""
+
+    def __init__(self, ctx, count):
+        self.ctx, self.count = ctx, int(count)
+        p = C.c_void_p()
+        _check(lib().p2b_malloc(ctx.handle, self.count * 8, C.byref(p)))
+        self.ptr = p.value
+
+    @classmethod
+    def from_host(cls, ctx, arr):
+        arr = _np(arr)
+        b = cls(ctx, arr.size)
+        if arr.size:
+            _check(lib().p2b_memcpy_h2d(ctx.handle, b.ptr, arr.ctypes.data, arr.size * 8))
+        return b
+
+    def to_host(self, count=None, offset=0):
+        count = self.count - offset if count is None else count
+        out = np.empty(count, dtype=np.uint64)
+        if count:
+            _check(lib().p2b_memcpy_d2h(self.ctx.handle, out.ctypes.data, self.ptr + 8 * offset, count * 8))
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib().p2b_free(self.ctx.handle, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PinnedBuffer:
+    """Page-locked host memory exposed as a numpy uint64 array (for the end-to-end benchmark leg)."""
+
+    def __init__(self, count):
+        p = C.c_void_p()
+        _check(lib().p2b_malloc_host(int(count) * 8, C.byref(p)))
+        self.ptr = p.value
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_uint64)), shape=(int(count),))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().p2b_free_host(self.ptr)
+            self.ptr = None
+
+
+class Context:
+    """Per-device context (replaces the reference's CudaInvContext, fri/oracle.rs:75-109)."""
+
+    def __init__(self, device=-1):
+        h = C.c_void_p()
+        _check(lib().p2b_ctx_create(device, C.byref(h)))
+        self.handle = h.value
+
+    def close(self):
+        if self.handle:
+            lib().p2b_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        _check(lib().p2b_ctx_synchronize(self.handle))
+
+    @property
+    def launch_count(self):
+        return int(lib().p2b_ctx_launch_count(self.handle))
+
+    def timer_start(self):
+        _check(lib().p2b_timer_start(self.handle))
+
+    def timer_stop_ms(self):
+        ms = C.c_float()
+        _check(lib().p2b_timer_stop_ms(self.handle, C.byref(ms)))
+        return float(ms.value)
+
+    # ---- building blocks ----
+    def field_op(self, op, a, b):
+        a, b = _np(a), _np(b)
+        da, db = DeviceBuffer.from_host(self, a), DeviceBuffer.from_host(self, b)
+        do = DeviceBuffer(self, a.size)
+        _check(lib().p2b_field_op(self.handle, {"add": 0, "sub": 1, "mul": 2, "mul_add": 3, "add_canonical": 4, "sub_canonical": 5}[op], da.ptr, db.ptr, do.ptr, a.size))
+        return do.to_host()
+
+    def poseidon(self, states):
+        s = _np(states).reshape(-1, 12)
+        d = DeviceBuffer.from_host(self, s)
+        _check(lib().p2b_poseidon_permute(self.handle, d.ptr, s.shape[0]))
+        return d.to_host().reshape(-1, 12)
+
+    def ifft(self, values):
+        """values [P][n] -> coefficients [P][n]  (values.into_par_iter().map(|v| v.ifft()))"""
+        v = _np(values)
+        P, n = v.shape
+        d = DeviceBuffer.from_host(self, v)
+        _check(lib().p2b_ifft_batch(self.handle, d.ptr, d.ptr, n.bit_length() - 1, P))
+        return d.to_host().reshape(P, n)
+
+    def lde_leaves(self, coeffs, rate_bits):
+        """coeffs [P][n] -> leaves [N][P] in the reference's leaf order"""
+        c = _np(coeffs)
+        P, n = c.shape
+        N = n << rate_bits
+        d = DeviceBuffer.from_host(self, c)
+        out = DeviceBuffer(self, N * P)
+        _check(lib().p2b_lde_leaves(self.handle, d.ptr, n.bit_length() - 1, P, rate_bits, out.ptr, P, 0))
+        return out.to_host().reshape(N, P)
+
+    def merkle_tree(self, leaves, cap_height):
+        """MerkleTree::new(leaves, cap_height) -> (digests [num_digests][4], cap [2^cap_height][4])"""
+        lv = _np(leaves)
+        N, ll = lv.shape
+        ncap = 1 << cap_height
+        nd = max(2 * (N - ncap), 0)
+        d = DeviceBuffer.from_host(self, lv)
+        dd, dc = DeviceBuffer(self, max(nd, 1) * 4), DeviceBuffer(self, max(ncap, 1) * 4)
+        _check(lib().p2b_merkle_tree(self.handle, d.ptr, N, ll, ll, 1, cap_height, dd.ptr, dc.ptr))
+        return dd.to_host(nd * 4).reshape(nd, 4), dc.to_host(ncap * 4).reshape(ncap, 4)
+
+    def fill_synthetic(self, dbuf, count, seed, first_index=0):
+        _check(lib().p2b_fill_synthetic(self.handle, dbuf.ptr, count, seed, first_index))
+
+
+class MerkleTree:
+    """View of a committed batch's tree (reference: MerkleTree {leaves, digests, cap}, merkle_tree.rs:41-66)."""
+
+    def __init__(self, batch):
+        self._b = batch
+
+    @property
+    def cap(self):
+        return self._b.cap()
+
+    @property
+    def digests(self):
+        return self._b.digests()
+
+    def get(self, i):
+        return self._b.leaves(i, 1)[0]
+
+    def prove(self, leaf_index):
+        return self._b.prove([leaf_index])[0]
+
+
+class PolynomialBatch:
+    """PolynomialBatch (fri/oracle.rs:112-120) resident on the device."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.handle = ctx, handle
+        info = BatchInfo()
+        _check(lib().p2b_batch_get_info(handle, C.byref(info)))
+        self.degree_log, self.rate_bits, self.cap_height = info.degree_log, info.rate_bits, info.cap_height
+        self.salt_size, self.num_polys, self.num_leaves = info.salt_size, info.num_polys, info.num_leaves
+        self.leaf_len, self.num_digests = info.leaf_len, info.num_digests
+        self.blinding = info.salt_size != 0
+        self.merkle_tree = MerkleTree(self)
+
+    @staticmethod
+    def _commit(fn, ctx, x, rate_bits, cap_height, salt, blinding):
+        if blinding and salt is None:
+            raise ValueError("blinding=True needs the salt columns [4][N] (the reference draws them at random)")
+        h = C.c_void_p()
+        if isinstance(x, DeviceBuffer):
+            raise TypeError("pass (DeviceBuffer, P, n) tuples for device-resident input")
+        if isinstance(x, tuple):
+            dbuf, P, n = x
+            ptr, on_host = dbuf.ptr, 0
+        else:
+            x = _np(x)
+            if x.ndim != 2 or x.shape[0] == 0:
+                raise P2BError(P2B_ERR_INVALID, "empty batch (no polynomials)")
+            P, n = x.shape
+            ptr, on_host = x.ctypes.data, 1
+        if n == 0 or n & (n - 1):
+            raise P2BError(P2B_ERR_INVALID, "polynomial length must be a power of two")
+        sp, s_host = None, 1
+        if salt is not None:
+            if isinstance(salt, DeviceBuffer):
+                sp, s_host = salt.ptr, 0
+            else:
+                salt = _np(salt)
+                assert salt.shape == (SALT_SIZE, n << rate_bits)
+                sp = salt.ctypes.data
+        _check(fn(ctx.handle, ptr, on_host, n.bit_length() - 1, P, rate_bits, cap_height, sp, s_host, C.byref(h)))
+        return PolynomialBatch(ctx, h.value)
+
+    @classmethod
+    def from_values(cls, ctx, values, rate_bits, cap_height, blinding=False, salt=None):
+        """fri/oracle.rs:709-731.  values: [P][n] numpy array (host) or (DeviceBuffer, P, n)."""
+        return cls._commit(lib().p2b_commit_from_values, ctx, values, rate_bits, cap_height, salt, blinding)
+
+    @classmethod
+    def from_coeffs(cls, ctx, coeffs, rate_bits, cap_height, blinding=False, salt=None):
+        """fri/oracle.rs:911-977."""
+        return cls._commit(lib().p2b_commit_from_coeffs, ctx, coeffs, rate_bits, cap_height, salt, blinding)
+
+    def close(self):
+        if self.handle:
+            lib().p2b_batch_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def device_ptrs(self):
+        a, b, c, d = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(lib().p2b_batch_device_ptrs(self.handle, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {"coeffs": a.value, "leaves": b.value, "digests": c.value, "cap": d.value}
+
+    def polynomials(self):
+        out = np.empty((self.num_polys, 1 << self.degree_log), dtype=np.uint64)
+        _check(lib().p2b_batch_get_coeffs(self.handle, out.ctypes.data))
+        return out
+
+    def cap(self, out=None):
+        out = np.empty((1 << self.cap_height, 4), dtype=np.uint64) if out is None else out
+        _check(lib().p2b_batch_get_cap(self.handle, out.ctypes.data))
+        return out
+
+    def digests(self):
+        out = np.empty((self.num_digests, 4), dtype=np.uint64)
+        if self.num_digests:
+            _check(lib().p2b_batch_get_digests(self.handle, out.ctypes.data))
+        return out
+
+    def leaves(self, first=0, count=None):
+        count = self.num_leaves - first if count is None else count
+        out = np.empty((count, self.leaf_len), dtype=np.uint64)
+        _check(lib().p2b_batch_get_leaves(self.handle, first, count, out.ctypes.data))
+        return out
+
+    def get_lde_values(self, index, step=1):
+        """fri/oracle.rs:1007-1018"""
+        out = np.empty(self.num_polys, dtype=np.uint64)
+        _check(lib().p2b_batch_get_lde_values(self.handle, index, step, out.ctypes.data))
+        return out
+
+    def prove(self, leaf_indices):
+        idx = _np(leaf_indices)
+        layers = self.degree_log + self.rate_bits - self.cap_height
+        out = np.empty((idx.size, layers, 4), dtype=np.uint64)
+        _check(lib().p2b_batch_prove(self.handle, idx.ctypes.data, idx.size, out.ctypes.data if layers else None))
+        return out
+
+    def open_rows(self, leaf_indices, with_proofs=True):
+        idx = _np(leaf_indices)
+        layers = self.degree_log + self.rate_bits - self.cap_height
+        rows = np.empty((idx.size, self.leaf_len), dtype=np.uint64)
+        sib = np.empty((idx.size, layers, 4), dtype=np.uint64) if with_proofs else None
+        _check(lib().p2b_batch_open_rows(self.handle, idx.ctypes.data, idx.size, rows.ctypes.data,
+                                         sib.ctypes.data if (with_proofs and layers) else None))
+        return rows, sib

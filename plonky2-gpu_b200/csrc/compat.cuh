@@ -1,0 +1,209 @@
+// compat.cuh -- the reference's own C symbols (cuda/src/lib.rs:52-145, cuda/plonky2_gpu.cu:57-785) on top of
+// the B200 kernels, so that the reference's Rust crate `plonky2_cuda` links against this library unchanged.
+// Included at the end of plonky2_b200.cu (single translation unit).
+//
+// Device-memory contract kept from the reference (plonky2/src/fri/oracle.rs:316-455,
+// cuda/plonky2_gpu.cu:435-606), element = u64, base = the pointer the caller passes:
+//   in : coefficients (or values for ifft) column-major at base[0 .. n*P)
+//   out: leaf-major LDE  base[0 .. N*P)            (row L = reference leaf L, bit-reversed order)
+//        work area       base[pad .. 2*pad)        (pad = pad_extvalues_len = N*(P+salt))
+//        digests, cap    base[2*pad .. 2*pad + 4*(num_digests + 2^cap_height))
+// `ctx` is the reference's {cudaStream_t stream, stream2} pair (plonky2_gpu.cu:4-7); stream2 carries the
+// caller's D2H copy of the coefficients, which must finish before base[0 .. n*P) is overwritten
+// (plonky2_gpu.cu:586).  Unlike the reference the shims do not printf, and they report launch errors.
+#pragma once
+
+struct RefStreams {
+  cudaStream_t stream;
+  cudaStream_t stream2;
+};
+
+static std::mutex g_compat_mu;
+static p2b_ctx* g_compat_ctx[64];
+
+static p2b_rust_error rust_ok() { return p2b_rust_error{0, nullptr}; }
+static p2b_rust_error rust_err(int rc) {
+  // code: a cudaError_t-like non-zero value; message strdup'd, freed by the Rust side (lib.rs:27-36)
+  const char* m = p2b_last_error();
+  return p2b_rust_error{rc == P2B_ERR_OOM ? (int)cudaErrorMemoryAllocation : (rc == P2B_ERR_INVALID ? (int)cudaErrorInvalidValue : (int)cudaErrorUnknown),
+                        m && *m ? strdup(m) : nullptr};
+}
+
+// one lazily created context per device for the legacy entry points; its main stream is replaced by the
+// caller's stream for the duration of a call (the reference launches everything on ctx->stream).
+static int compat_ctx(void* ref_ctx, p2b_ctx** out, cudaStream_t* saved) {
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(P2B_ERR_INVALID, "device index %d", dev);
+  std::lock_guard<std::mutex> lk(g_compat_mu);
+  if (!g_compat_ctx[dev]) P2B_TRY(p2b_ctx_create(dev, &g_compat_ctx[dev]));
+  p2b_ctx* c = g_compat_ctx[dev];
+  *saved = c->stream;
+  if (ref_ctx) {
+    cudaStream_t s = static_cast<RefStreams*>(ref_ctx)->stream;
+    if (s) c->stream = s;
+  }
+  *out = c;
+  return P2B_OK;
+}
+
+extern "C" void init(void) {
+  p2b_ctx* c;
+  cudaStream_t saved;
+  if (compat_ctx(nullptr, &c, &saved) == P2B_OK) c->stream = saved;
+}
+
+// ifft: in-place inverse NTT of poly_num columns (cuda/plonky2_gpu.cu:70-86; oracle.rs:394-401)
+extern "C" p2b_rust_error ifft(uint64_t* d_values_flatten, int poly_num, int values_num_per_poly, int log_len,
+                               const uint64_t* d_root_table, const uint64_t* p_inv, void* ctx) {
+  (void)d_root_table;
+  (void)p_inv;
+  if (!d_values_flatten || poly_num <= 0 || log_len < 0 || values_num_per_poly != (1 << log_len)) {
+    fail(P2B_ERR_INVALID, "ifft: bad arguments");
+    return rust_err(P2B_ERR_INVALID);
+  }
+  p2b_ctx* c;
+  cudaStream_t saved;
+  int rc = compat_ctx(ctx, &c, &saved);
+  if (rc != P2B_OK) return rust_err(rc);
+  rc = p2b_ifft_batch(c, d_values_flatten, d_values_flatten, (u32)log_len, (u64)poly_num);
+  if (rc == P2B_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(P2B_ERR_CUDA, "ifft: stream synchronize failed");
+  c->stream = saved;
+  return rc == P2B_OK ? rust_ok() : rust_err(rc);
+}
+
+static int compat_from_coeffs(p2b_ctx* c, RefStreams* rs, u64* base, int poly_num, int log_len, int rate_bits,
+                              int salt_size, int cap_height, long long pad) {
+  if (salt_size != 0)
+    return fail(P2B_ERR_UNSUPPORTED, "legacy entry points do not carry blinding columns; use p2b_commit_* with a salt");
+  const u64 P = (u64)poly_num, n = (u64)1 << log_len, N = n << rate_bits;
+  if ((u64)pad < N * P) return fail(P2B_ERR_INVALID, "pad_extvalues_len smaller than the LDE matrix");
+  const u64 ncap = (u64)1 << cap_height;
+  u64* work = base + pad;
+  u64* digests = work + N * (P + (u64)salt_size);  // d_digest_buf, plonky2_gpu.cu:552
+  u64* cap = digests + 4 * 2 * (N - ncap);
+  const u64* coeffs = base;
+  if (make_plan((u32)log_len).n_strided == 0) {
+    // tiny transforms have a single pass that would read the coefficients while other CTAs overwrite them
+    CUDA_TRY(cudaMemcpyAsync(work, base, n * P * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+    coeffs = work;
+  }
+  // intermediates live in the work area; coset blocks are produced in descending order so that block 0,
+  // whose rows overwrite the coefficients, is written last and only after stream2's copy has finished.
+  return lde_and_merkle(c, coeffs, (u32)log_len, P, (u32)rate_bits, (u32)cap_height, nullptr, work, base, P, digests, cap,
+                        true, rs ? rs->stream2 : nullptr);
+}
+
+// merkle_tree_from_coeffs (cuda/plonky2_gpu.cu:435-606; oracle.rs:409-422, 599-627)
+extern "C" p2b_rust_error merkle_tree_from_coeffs(uint64_t* d_values_flatten, uint64_t* d_ext_values_flatten, int poly_num,
+                                                  int values_num_per_poly, int log_len, const uint64_t* d_root_table,
+                                                  const uint64_t* d_root_table2, const uint64_t* d_shift_powers,
+                                                  int rate_bits, int salt_size, int cap_height, int pad_extvalues_len,
+                                                  void* ctx) {
+  (void)d_root_table;
+  (void)d_root_table2;
+  (void)d_shift_powers;
+  if (!d_values_flatten || d_ext_values_flatten != d_values_flatten || poly_num <= 0 || log_len < 0 ||
+      values_num_per_poly != (1 << log_len) || rate_bits < 0 || cap_height < 0 || cap_height > log_len + rate_bits) {
+    fail(P2B_ERR_INVALID, "merkle_tree_from_coeffs: bad arguments (the reference passes the same pointer for values and ext_values)");
+    return rust_err(P2B_ERR_INVALID);
+  }
+  p2b_ctx* c;
+  cudaStream_t saved;
+  int rc = compat_ctx(ctx, &c, &saved);
+  if (rc != P2B_OK) return rust_err(rc);
+  rc = compat_from_coeffs(c, static_cast<RefStreams*>(ctx), d_values_flatten, poly_num, log_len, rate_bits, salt_size, cap_height,
+                          pad_extvalues_len);
+  if (rc == P2B_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(P2B_ERR_CUDA, "stream synchronize failed");
+  c->stream = saved;
+  return rc == P2B_OK ? rust_ok() : rust_err(rc);
+}
+
+// merkle_tree_from_values (declared lib.rs:83-98; the reference's body is `assert(0)`, plonky2_gpu.cu:228):
+// implemented here as ifft followed by merkle_tree_from_coeffs, which is what its dead code intended.
+extern "C" p2b_rust_error merkle_tree_from_values(uint64_t* d_values_flatten, uint64_t* d_ext_values_flatten, int poly_num,
+                                                  int values_num_per_poly, int log_len, const uint64_t* d_root_table,
+                                                  const uint64_t* d_root_table2, const uint64_t* d_shift_powers,
+                                                  const uint64_t* p_inv, int rate_bits, int salt_size, int cap_height,
+                                                  int pad_extvalues_len, void* ctx) {
+  p2b_rust_error e = ifft(d_values_flatten, poly_num, values_num_per_poly, log_len, d_root_table, p_inv, ctx);
+  if (e.code != 0) return e;
+  return merkle_tree_from_coeffs(d_values_flatten, d_ext_values_flatten, poly_num, values_num_per_poly, log_len, d_root_table,
+                                 d_root_table2, d_shift_powers, rate_bits, salt_size, cap_height, pad_extvalues_len, ctx);
+}
+
+// build_merkle_tree (lib.rs:71-81; plonky2_gpu.cu:138-189): the reference takes the column-major, natural-order
+// LDE in the work area base[pad ..], bit-reverses it in place, and builds digests + cap behind it.  Here the
+// leaves are hashed straight from the column-major matrix with the bit-reversed row index, then the matrix is
+// permuted so the work area ends in the state the reference leaves it in.
+__global__ void bitrev_rows_colmajor_kernel(u64* __restrict__ m, u64 N, u32 log_N, u64 ncols) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  u64 col = blockIdx.y;
+  if (i >= N) return;
+  u64 j = log_N ? (__brevll(i) >> (64 - log_N)) : 0;
+  if (i < j) {
+    u64* p = m + col * N;
+    u64 a = p[i], b = p[j];
+    p[i] = b;
+    p[j] = a;
+  }
+}
+extern "C" p2b_rust_error build_merkle_tree(uint64_t* d_ext_values_flatten, int poly_num, int values_num_per_poly, int log_len,
+                                            int rate_bits, int salt_size, int cap_height, int pad_extvalues_len, void* ctx) {
+  if (!d_ext_values_flatten || poly_num <= 0 || log_len < 0 || values_num_per_poly != (1 << log_len) || rate_bits < 0 ||
+      salt_size < 0 || cap_height < 0 || cap_height > log_len + rate_bits) {
+    fail(P2B_ERR_INVALID, "build_merkle_tree: bad arguments");
+    return rust_err(P2B_ERR_INVALID);
+  }
+  p2b_ctx* c;
+  cudaStream_t saved;
+  int rc = compat_ctx(ctx, &c, &saved);
+  if (rc != P2B_OK) return rust_err(rc);
+  const u64 N = (u64)values_num_per_poly << rate_bits, cols = (u64)poly_num + salt_size;
+  const u32 log_N = (u32)(log_len + rate_bits);
+  u64* m = d_ext_values_flatten + pad_extvalues_len;
+  u64* digests = m + N * cols;
+  u64* cap = digests + 4 * 2 * (N - ((u64)1 << cap_height));
+  dim3 grid((unsigned)((N + 255) / 256), (unsigned)cols);
+  bitrev_rows_colmajor_kernel<<<grid, 256, 0, c->stream>>>(m, N, log_N, cols);
+  c->launches++;
+  if (cudaGetLastError() != cudaSuccess) rc = fail(P2B_ERR_CUDA, "bit-reversal launch failed");
+  if (rc == P2B_OK) rc = p2b_merkle_tree(c, m, N, cols, 1, N, (u32)cap_height, digests, cap);
+  if (rc == P2B_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(P2B_ERR_CUDA, "stream synchronize failed");
+  c->stream = saved;
+  return rc == P2B_OK ? rust_ok() : rust_err(rc);
+}
+
+// transpose (plonky2_gpu.cu:192-215): column-major [cols][N] in the work area -> row-major [N][cols] at base.
+__global__ void transpose_to_rows_kernel(const u64* __restrict__ src, u64* __restrict__ dst, u64 N, u64 cols) {
+  __shared__ u64 tile[32][33];
+  u64 r0 = (u64)blockIdx.x * 32, c0 = (u64)blockIdx.y * 32;
+  for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+    u64 c = c0 + k, r = r0 + threadIdx.x;
+    if (c < cols && r < N) tile[k][threadIdx.x] = src[c * N + r];
+  }
+  __syncthreads();
+  for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+    u64 r = r0 + k, c = c0 + threadIdx.x;
+    if (c < cols && r < N) dst[r * cols + c] = tile[threadIdx.x][k];
+  }
+}
+extern "C" p2b_rust_error transpose(uint64_t* d_ext_values_flatten, int poly_num, int values_num_per_poly, int rate_bits,
+                                    int salt_size, int pad_extvalues_len, void* ctx) {
+  if (!d_ext_values_flatten || poly_num <= 0 || values_num_per_poly <= 0 || rate_bits < 0 || salt_size < 0) {
+    fail(P2B_ERR_INVALID, "transpose: bad arguments");
+    return rust_err(P2B_ERR_INVALID);
+  }
+  p2b_ctx* c;
+  cudaStream_t saved;
+  int rc = compat_ctx(ctx, &c, &saved);
+  if (rc != P2B_OK) return rust_err(rc);
+  const u64 N = (u64)values_num_per_poly << rate_bits, cols = (u64)poly_num + salt_size;
+  dim3 grid((unsigned)((N + 31) / 32), (unsigned)((cols + 31) / 32)), block(32, 8);
+  transpose_to_rows_kernel<<<grid, block, 0, c->stream>>>(d_ext_values_flatten + pad_extvalues_len, d_ext_values_flatten, N, cols);
+  c->launches++;
+  if (cudaGetLastError() != cudaSuccess) rc = fail(P2B_ERR_CUDA, "transpose launch failed");
+  if (rc == P2B_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(P2B_ERR_CUDA, "stream synchronize failed");
+  c->stream = saved;
+  return rc == P2B_OK ? rust_ok() : rust_err(rc);
+}

@@ -1,0 +1,133 @@
+// merkle.cuh -- Poseidon Merkle tree over leaf rows: leaf hashing, digest layers, cap.
+//
+// Reference semantics: MerkleTree::new / fill_digests_buf / fill_subtree
+// (plonky2/src/hash/merkle_tree.rs:283-319, 210-244, 78-105); leaf digest = hash_or_noop
+// (plonk/config.rs:56-67) over the overwrite-mode sponge hash_n_to_m_no_pad (hash/hashing.rs:81-104);
+// inner node = two_to_one (hashing.rs:65-72).
+//
+// Digest layout (merkle_tree.rs:46-54, 424-435): `digests` = 2^cap_height sub-trees of
+// 2*(leaves_per_subtree - 1) hashes each; inside a sub-tree the node at layer l (0 = leaf digests),
+// position q sits at  2*(((q >> 1) << (l + 1)) + 2^l - 1) + (q & 1);  sub-tree roots go to cap[t].
+// The closed form replaces the reference CUDA's per-access loop (cuda/plonky2_gpu_impl.cuh:315-348).
+//
+// B200 mapping: one thread per leaf / per node, sponge state in registers, all sub-trees of a layer in
+// one launch (the reference launches one 256-thread block per sub-tree, i.e. 16 SMs).  The kernels are
+// integer-issue bound (about 2*10^4 instructions per permutation versus 64 B of input), so loads go
+// straight through L1 with no shared-memory staging.
+#pragma once
+#include "poseidon.cuh"
+
+namespace merkle {
+
+using gl::u32;
+using gl::u64;
+
+struct TreeShape {
+  u64 num_leaves;     // N (power of two)
+  u32 log_leaves;     // log2 N
+  u32 cap_height;     // c
+  u32 sub_log;        // log2(N) - c  : layers below the cap
+  u64 sub_digests;    // 2 * (N / 2^c - 1)
+};
+
+__host__ __device__ __forceinline__ TreeShape make_shape(u32 log_leaves, u32 cap_height) {
+  TreeShape t;
+  t.num_leaves = (u64)1 << log_leaves;
+  t.log_leaves = log_leaves;
+  t.cap_height = cap_height;
+  t.sub_log = log_leaves - cap_height;
+  t.sub_digests = 2 * (((u64)1 << t.sub_log) - 1);
+  return t;
+}
+
+// Where node Q of layer l (Q counted across the whole tree, 0 <= Q < N / 2^l) is stored: a pointer into
+// `digests` or, for sub-tree roots (l == sub_log), into `cap`.
+__device__ __forceinline__ u64* node_slot(const TreeShape& t, u64* digests, u64* cap, u32 l, u64 Q) {
+  if (l == t.sub_log) return cap + 4 * Q;
+  u32 bits = t.sub_log - l;                    // log2(nodes of this layer per sub-tree)
+  u64 tree = Q >> bits;
+  u64 q = Q & (((u64)1 << bits) - 1);
+  u64 idx = 2 * (((q >> 1) << (l + 1)) + ((u64)1 << l) - 1) + (q & 1);
+  return digests + 4 * (tree * t.sub_digests + idx);
+}
+
+__device__ __forceinline__ void store_hash(u64* dst, const u64 h[4]) {
+  // 32-byte aligned slot -> two 16-byte stores
+  reinterpret_cast<ulonglong2*>(dst)[0] = make_ulonglong2(h[0], h[1]);
+  reinterpret_cast<ulonglong2*>(dst)[1] = make_ulonglong2(h[2], h[3]);
+}
+__device__ __forceinline__ void load_hash(const u64* src, u64 h[4]) {
+  ulonglong2 a = reinterpret_cast<const ulonglong2*>(src)[0];
+  ulonglong2 b = reinterpret_cast<const ulonglong2*>(src)[1];
+  h[0] = a.x; h[1] = a.y; h[2] = b.x; h[3] = b.y;
+}
+
+// hash_or_noop of one leaf whose element j is at base[j * col_stride].  Result canonical.
+__device__ __forceinline__ void hash_leaf(const u64* __restrict__ base, u64 col_stride, u32 leaf_len, u64 out[4]) {
+  if (leaf_len <= 4) {  // plonk/config.rs:57-63: copy canonical values, zero pad
+#pragma unroll
+    for (u32 i = 0; i < 4; i++) out[i] = i < leaf_len ? gl::canon(__ldg(base + i * col_stride)) : 0;
+    return;
+  }
+  u64 s[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = 0;
+  u32 full = leaf_len / 8, rem = leaf_len % 8;
+  const u64* p = base;
+#pragma unroll 1
+  for (u32 k = 0; k < full; k++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = __ldg(p + i * col_stride);
+    p += 8 * col_stride;
+    poseidon::permute(s);
+  }
+  if (rem) {  // partial last chunk overwrites only `rem` lanes (hashing.rs:88-91)
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      if ((u32)i < rem) s[i] = __ldg(p + i * col_stride);
+    poseidon::permute(s);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) out[i] = gl::canon(s[i]);
+}
+
+// One thread per leaf.  leaves element (row, col) at leaves[row * row_stride + col * col_stride].
+// leaf_index0: global index of this launch's first leaf (multi-GPU shards / coset blocks hash a sub-range
+// of the tree's leaves but write into the whole tree's layout).
+__global__ void __launch_bounds__(128)
+hash_leaves_kernel(const u64* __restrict__ leaves, u64 row_stride, u64 col_stride, u32 leaf_len, u64 count,
+                   u64 leaf_index0, TreeShape shape, u64* __restrict__ digests, u64* __restrict__ cap) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  u64 h[4];
+  hash_leaf(leaves + i * row_stride, col_stride, leaf_len, h);
+  store_hash(node_slot(shape, digests, cap, 0, leaf_index0 + i), h);
+}
+
+// One thread per node of layer `l` (l >= 1): parent of nodes 2Q, 2Q+1 of layer l-1.
+__global__ void __launch_bounds__(128)
+merkle_layer_kernel(TreeShape shape, u32 l, u64 node0, u64 count, u64* __restrict__ digests, u64* __restrict__ cap) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  u64 Q = node0 + i;
+  const u64* left = node_slot(shape, digests, cap, l - 1, 2 * Q);  // siblings are adjacent: left + 4
+  u64 a[4], b[4], h[4];
+  load_hash(left, a);
+  load_hash(left + 4, b);
+  poseidon::two_to_one(a, b, h);
+  store_hash(node_slot(shape, digests, cap, l, Q), h);
+}
+
+// Batched permutation (test / micro-benchmark entry): states[i][12] -> permuted, canonical.
+__global__ void __launch_bounds__(128) permute_kernel(u64* __restrict__ states, u64 count, int reps) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  u64 s[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) s[k] = states[i * 12 + k];
+  for (int r = 0; r < reps; r++) poseidon::permute(s);
+#pragma unroll
+  for (int k = 0; k < 12; k++) states[i * 12 + k] = gl::canon(s[k]);
+}
+
+}  // namespace merkle

@@ -1,0 +1,826 @@
+// plonky2_b200.cu -- the library's single translation unit: context, pass planner, commit orchestration
+// and the C ABI declared in include/plonky2_b200.h.
+//
+// Path implemented (reference file:line):
+//   PolynomialBatch::from_values   plonky2/src/fri/oracle.rs:709-731
+//   PolynomialBatch::from_coeffs   plonky2/src/fri/oracle.rs:911-977  (lde_values :979-1004)
+//   MerkleTree::new / prove        plonky2/src/hash/merkle_tree.rs:283-319, 392-440
+//   get_lde_values                 plonky2/src/fri/oracle.rs:1007-1018
+// and the boundary the reference's Rust side binds: cuda/src/lib.rs:52-145.
+//
+// HBM layout of a committed batch (one cudaMallocAsync block each, 256-byte aligned):
+//   coeffs  [P][n]            column-major, natural coefficient order           8 n P bytes
+//   leaves  [N][P + salt]     row-major, reference leaf order (bit-reversed)     8 N (P+salt) bytes
+//   digests [2 (N - 2^c)][4]  reference recursive layout                         64 (N - 2^c) bytes
+//   cap     [2^c][4]
+// plus a context-owned scratch [P][n] that holds one coset block between its NTT passes.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/plonky2_b200.h"
+#include "merkle.cuh"
+#include "ntt.cuh"
+
+using gl::u32;
+using gl::u64;
+
+// ======================================================================================================
+// errors
+// ======================================================================================================
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return fail(_e == cudaErrorMemoryAllocation ? P2B_ERR_OOM : P2B_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, \
+                  cudaGetErrorString(_e), __FILE__, __LINE__);                                      \
+  } while (0)
+#define P2B_TRY(expr)           \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != P2B_OK) return _rc; \
+  } while (0)
+
+extern "C" const char* p2b_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* p2b_version(void) { return "plonky2_b200 0.1 sm_100a"; }
+
+// ======================================================================================================
+// host-side field helpers (table set-up only)
+// ======================================================================================================
+namespace hostf {
+typedef unsigned __int128 u128;
+static inline u64 mul(u64 a, u64 b) { return (u64)(((u128)a * b) % gl::P); }
+static inline u64 pow(u64 b, u64 e) {
+  u64 r = 1;
+  while (e) {
+    if (e & 1) r = mul(r, b);
+    b = mul(b, b);
+    e >>= 1;
+  }
+  return r;
+}
+static inline u64 inv(u64 a) { return pow(a, gl::P - 2); }
+// primitive_root_of_unity (field/src/types.rs:268-272), POWER_OF_TWO_GENERATOR goldilocks_field.rs:89
+static inline u64 root(unsigned n_log) {
+  u64 b = 1753635133440165772ull;
+  for (unsigned i = 0; i < 32 - n_log; i++) b = mul(b, b);
+  return b;
+}
+static constexpr u64 COSET_SHIFT = 7;  // MULTIPLICATIVE_GROUP_GENERATOR, goldilocks_field.rs:82
+}  // namespace hostf
+
+// ======================================================================================================
+// context
+// ======================================================================================================
+struct p2b_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;   // NTT passes, tree layers, copies
+  cudaStream_t stream2 = nullptr;  // leaf hashing of block b overlaps the NTT of block b+1
+  bool owns_streams = true;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  std::vector<cudaEvent_t> ev_pool;
+  // twiddle tables U[b], b < 2^tw_log  (forward and inverse roots)
+  u64* U_fwd = nullptr;
+  u64* U_inv = nullptr;
+  u64* d_roots = nullptr;  // [2][34]
+  u32 tw_log = 0;
+  // scratch
+  u64* scratch = nullptr;
+  u64 scratch_elems = 0;
+  u64 launches = 0;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+};
+
+static int ensure_scratch(p2b_ctx* c, u64 elems) {
+  if (c->scratch_elems >= elems) return P2B_OK;
+  if (c->scratch) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream2));
+    CUDA_TRY(cudaFree(c->scratch));
+    c->scratch = nullptr;
+    c->scratch_elems = 0;
+  }
+  CUDA_TRY(cudaMalloc(&c->scratch, elems * sizeof(u64)));
+  c->scratch_elems = elems;
+  return P2B_OK;
+}
+
+static int ensure_twiddles(p2b_ctx* c, u32 log_count) {
+  if (log_count < 4) log_count = 4;
+  if (c->tw_log >= log_count) return P2B_OK;
+  if (log_count > 31) return fail(P2B_ERR_INVALID, "transform too large: twiddle table 2^%u", log_count);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream2));
+  if (c->U_fwd) CUDA_TRY(cudaFree(c->U_fwd));
+  if (c->U_inv) CUDA_TRY(cudaFree(c->U_inv));
+  c->U_fwd = c->U_inv = nullptr;
+  c->tw_log = 0;
+  u64 count = (u64)1 << log_count;
+  CUDA_TRY(cudaMalloc(&c->U_fwd, count * sizeof(u64)));
+  CUDA_TRY(cudaMalloc(&c->U_inv, count * sizeof(u64)));
+  if (!c->d_roots) {
+    u64 h[2][34];
+    for (int j = 0; j < 34; j++) {
+      u64 r = j <= 32 ? hostf::root(j) : 1;
+      h[0][j] = r;
+      h[1][j] = hostf::inv(r);
+    }
+    CUDA_TRY(cudaMalloc(&c->d_roots, sizeof(h)));
+    CUDA_TRY(cudaMemcpyAsync(c->d_roots, h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+  }
+  unsigned blocks = (unsigned)((count + 255) / 256);
+  ntt::build_twiddles_kernel<<<blocks, 256, 0, c->stream>>>(c->U_fwd, count, c->d_roots);
+  ntt::build_twiddles_kernel<<<blocks, 256, 0, c->stream>>>(c->U_inv, count, c->d_roots + 34);
+  c->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  c->tw_log = log_count;
+  return P2B_OK;
+}
+
+template <typename K>
+static int opt_in_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return P2B_OK;
+}
+
+static int ctx_init_common(p2b_ctx* c) {
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, c->device));
+  if (prop.major < 10)
+    return fail(P2B_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", c->device,
+                prop.major, prop.minor);
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  CUDA_TRY(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreate(&c->ev_t0));
+  CUDA_TRY(cudaEventCreate(&c->ev_t1));
+  CUDA_TRY(poseidon::upload_constants());
+  // let the stream-ordered pool keep its memory between commits (no OS round trip inside a timed step)
+  cudaMemPool_t pool;
+  CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, c->device));
+  uint64_t thresh = UINT64_MAX;
+  CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  return P2B_OK;
+}
+
+extern "C" int p2b_ctx_create(int device, p2b_ctx** out) {
+  if (!out) return fail(P2B_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (ndev == 0) return fail(P2B_ERR_CUDA, "no CUDA device");
+  if (device < 0) CUDA_TRY(cudaGetDevice(&device));
+  if (device >= ndev) return fail(P2B_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
+  CUDA_TRY(cudaSetDevice(device));
+  p2b_ctx* c = new (std::nothrow) p2b_ctx();
+  if (!c) return fail(P2B_ERR_OOM, "host allocation failed");
+  c->device = device;
+  int rc = P2B_OK;
+  cudaError_t e;
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking)) != cudaSuccess)
+    rc = fail(P2B_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+  if (rc == P2B_OK) rc = ctx_init_common(c);
+  if (rc != P2B_OK) {
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return P2B_OK;
+}
+
+extern "C" void p2b_ctx_destroy(p2b_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->stream2) cudaStreamSynchronize(c->stream2);
+  cudaFree(c->U_fwd);
+  cudaFree(c->U_inv);
+  cudaFree(c->d_roots);
+  cudaFree(c->scratch);
+  for (cudaEvent_t e : {c->ev_a, c->ev_b, c->ev_t0, c->ev_t1})
+    if (e) cudaEventDestroy(e);
+  if (c->owns_streams) {
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
+  }
+  delete c;
+}
+
+extern "C" void* p2b_ctx_stream(p2b_ctx* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" int p2b_ctx_synchronize(p2b_ctx* c) {
+  if (!c) return fail(P2B_ERR_INVALID, "ctx is NULL");
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream2));
+  return P2B_OK;
+}
+extern "C" uint64_t p2b_ctx_launch_count(const p2b_ctx* c) { return c ? c->launches : 0; }
+
+// ======================================================================================================
+// pass planner
+// ======================================================================================================
+static constexpr u32 FINAL_L = 9;      // levels of the last pass (512-row chunks)
+static constexpr u32 STRIDED_MAX_L = 11;
+static constexpr int FINAL_C = 8;      // columns per CTA in the final LDE / column-major pass
+static constexpr int INTT_J = 16;      // chunks per CTA in the inverse final pass
+
+struct Plan {
+  u32 k;
+  u32 n_strided;
+  u32 s0[4], L[4];  // strided passes
+  u32 final_s0, final_L;
+};
+static Plan make_plan(u32 k) {
+  Plan p{};
+  p.k = k;
+  p.final_L = k < FINAL_L ? k : FINAL_L;
+  p.final_s0 = k - p.final_L;
+  u32 rem = p.final_s0;
+  p.n_strided = (rem + STRIDED_MAX_L - 1) / STRIDED_MAX_L;
+  u32 s = 0;
+  for (u32 i = 0; i < p.n_strided; i++) {
+    u32 left = p.n_strided - i;
+    u32 L = (rem + left - 1) / left;
+    p.s0[i] = s;
+    p.L[i] = L;
+    s += L;
+    rem -= L;
+  }
+  return p;
+}
+
+static int launch_strided(p2b_ctx* c, cudaStream_t st, const ntt::PassArgs& a, const ntt::LevelScale& sc) {
+  const u64 stride = ((u64)1 << a.k) >> (a.s0 + a.L);
+  // T = 16 positions (128-byte segments) unless the tile would not fit in shared memory
+  size_t smem16 = ((size_t)(16 + 1) << a.L) * 8;
+  bool use16 = stride >= 16 && smem16 <= c->smem_optin;
+  int T = use16 ? 16 : 8;
+  if (stride < (u64)T) return fail(P2B_ERR_INVALID, "internal: strided pass with stride %llu", (unsigned long long)stride);
+  size_t smem = ((size_t)(T + 1) << a.L) * 8;
+  if (smem > c->smem_optin) return fail(P2B_ERR_INVALID, "internal: strided tile does not fit shared memory");
+  u64 tiles = ((u64)1 << a.s0) * (stride / T);
+  dim3 grid((unsigned)tiles, a.ncols);
+  if (use16) {
+    P2B_TRY(opt_in_smem(ntt::ntt_strided_pass_kernel<16>, smem));
+    ntt::ntt_strided_pass_kernel<16><<<grid, 512, smem, st>>>(a, sc);
+  } else {
+    P2B_TRY(opt_in_smem(ntt::ntt_strided_pass_kernel<8>, smem));
+    ntt::ntt_strided_pass_kernel<8><<<grid, 512, smem, st>>>(a, sc);
+  }
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return P2B_OK;
+}
+
+// ======================================================================================================
+// inverse NTT of P columns: src [P][n] -> dst [P][n] (natural order, scaled).  tmp: [P][n] scratch, needed
+// when the plan has strided passes and src must be preserved (tmp may equal dst when src != dst is not
+// required to survive).
+// ======================================================================================================
+static int run_ifft(p2b_ctx* c, const u64* src, u64* dst, u64* tmp, u32 k, u64 P) {
+  if (P == 0) return P2B_OK;
+  P2B_TRY(ensure_twiddles(c, k > 0 ? k - 1 : 0));
+  Plan pl = make_plan(k);
+  const u64 n = (u64)1 << k;
+  ntt::LevelScale sc{};
+  ntt::PassArgs a{};
+  a.k = k;
+  a.block_base = 0;
+  a.U = c->U_inv;
+  a.scaled = 0;
+  a.ncols = (u32)P;
+  const u64* cur = src;
+  for (u32 i = 0; i < pl.n_strided; i++) {
+    a.src = cur;
+    a.dst = tmp;
+    a.src_cs = n;
+    a.dst_cs = n;
+    a.s0 = pl.s0[i];
+    a.L = pl.L[i];
+    P2B_TRY(launch_strided(c, c->stream, a, sc));
+    cur = tmp;
+  }
+  a.src = cur;
+  a.dst = dst;
+  a.src_cs = a.dst_cs = n;
+  a.s0 = pl.final_s0;
+  a.L = pl.final_L;
+  size_t smem = ((size_t)INTT_J << a.L) * 8;
+  P2B_TRY(opt_in_smem(ntt::intt_final_pass_kernel<INTT_J>, smem));
+  u64 chunks = (u64)1 << a.s0;
+  dim3 grid((unsigned)((chunks + INTT_J - 1) / INTT_J), (unsigned)P);
+  ntt::intt_final_pass_kernel<INTT_J><<<grid, 512, smem, c->stream>>>(a, gl::inverse_2exp(k));
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return P2B_OK;
+}
+
+// sigma[s] = g^(n / 2^(s+1)) for the LDE sub-problem of size n = 2^k
+static ntt::LevelScale lde_scale(u32 k) {
+  ntt::LevelScale sc{};
+  for (u32 s = 0; s < k; s++) sc.sigma[s] = hostf::pow(hostf::COSET_SHIFT, ((u64)1 << k) >> (s + 1));
+  return sc;
+}
+
+// One coset block b of the LDE: coeffs [P][n] -> rows [b*n, (b+1)*n) of leaves (row-major).
+static int run_lde_block(p2b_ctx* c, cudaStream_t st, const u64* coeffs, u64 coeffs_cs, u64* tmp, u32 k, u64 P,
+                         u64 b, const ntt::LevelScale& sc, u64* leaves, u64 row_stride, u64 col0) {
+  Plan pl = make_plan(k);
+  const u64 n = (u64)1 << k;
+  ntt::PassArgs a{};
+  a.k = k;
+  a.block_base = b;
+  a.U = c->U_fwd;
+  a.scaled = 1;
+  a.ncols = (u32)P;
+  const u64* cur = coeffs;
+  u64 cur_cs = coeffs_cs;
+  for (u32 i = 0; i < pl.n_strided; i++) {
+    a.src = cur;
+    a.src_cs = cur_cs;
+    a.dst = tmp;
+    a.dst_cs = n;
+    a.s0 = pl.s0[i];
+    a.L = pl.L[i];
+    P2B_TRY(launch_strided(c, st, a, sc));
+    cur = tmp;
+    cur_cs = n;
+  }
+  a.src = cur;
+  a.src_cs = cur_cs;
+  a.dst = leaves;
+  a.dst_cs = 0;
+  a.s0 = pl.final_s0;
+  a.L = pl.final_L;
+  size_t smem = (((size_t)(FINAL_C + 1) << a.L) + ((size_t)1 << a.L)) * 8;
+  P2B_TRY(opt_in_smem(ntt::ntt_final_pass_kernel<FINAL_C, ntt::MODE_ROWS>, smem));
+  dim3 grid((unsigned)((u64)1 << a.s0), (unsigned)((P + FINAL_C - 1) / FINAL_C));
+  ntt::ntt_final_pass_kernel<FINAL_C, ntt::MODE_ROWS><<<grid, 512, smem, st>>>(a, sc, b * n, row_stride, col0);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return P2B_OK;
+}
+
+// ======================================================================================================
+// Merkle tree over leaf rows
+// ======================================================================================================
+static int launch_hash_leaves(p2b_ctx* c, cudaStream_t st, const u64* leaves, u64 row_stride, u64 col_stride,
+                              u32 leaf_len, u64 first_leaf, u64 count, const merkle::TreeShape& shape, u64* digests,
+                              u64* cap) {
+  if (count == 0) return P2B_OK;
+  unsigned blocks = (unsigned)((count + 127) / 128);
+  merkle::hash_leaves_kernel<<<blocks, 128, 0, st>>>(leaves + first_leaf * row_stride, row_stride, col_stride, leaf_len,
+                                                     count, first_leaf, shape, digests, cap);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return P2B_OK;
+}
+static int launch_layers(p2b_ctx* c, cudaStream_t st, const merkle::TreeShape& shape, u64* digests, u64* cap) {
+  for (u32 l = 1; l <= shape.sub_log; l++) {
+    u64 count = shape.num_leaves >> l;
+    unsigned blocks = (unsigned)((count + 127) / 128);
+    merkle::merkle_layer_kernel<<<blocks, 128, 0, st>>>(shape, l, 0, count, digests, cap);
+    c->launches++;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return P2B_OK;
+}
+
+// leaf row L, column P + c  <-  salt[c][reverse_bits(L)]   (oracle.rs:998-1002 then :942-952)
+__global__ void scatter_salt_kernel(const u64* __restrict__ salt, u64 N, u32 log_N, u64* __restrict__ leaves,
+                                    u64 row_stride, u64 col0) {
+  u64 L = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (L >= N) return;
+  u64 src = log_N ? (__brevll(L) >> (64 - log_N)) : 0;
+#pragma unroll
+  for (int cidx = 0; cidx < P2B_SALT_SIZE; cidx++) leaves[L * row_stride + col0 + cidx] = gl::canon(salt[(u64)cidx * N + src]);
+}
+
+// ======================================================================================================
+// batch
+// ======================================================================================================
+struct p2b_batch {
+  p2b_ctx* ctx = nullptr;
+  p2b_batch_info info{};
+  u64* coeffs = nullptr;
+  u64* leaves = nullptr;
+  u64* digests = nullptr;
+  u64* cap = nullptr;
+  merkle::TreeShape shape{};
+};
+
+static int batch_free(p2b_batch* b) {
+  if (!b) return P2B_OK;
+  cudaStream_t st = b->ctx->stream;
+  if (b->coeffs) cudaFreeAsync(b->coeffs, st);
+  if (b->leaves) cudaFreeAsync(b->leaves, st);
+  if (b->digests) cudaFreeAsync(b->digests, st);
+  if (b->cap) cudaFreeAsync(b->cap, st);
+  delete b;
+  return P2B_OK;
+}
+extern "C" void p2b_batch_destroy(p2b_batch* b) { batch_free(b); }
+
+// The LDE + Merkle part shared by from_values / from_coeffs and the compat shims.
+//   coeffs_d [P][n] (device) -> leaves_d, digests_d, cap_d.   `descending`: process coset blocks b = R-1..0
+//   (needed when leaves_d aliases coeffs_d: block 0's rows overwrite the coefficients last).
+static int lde_and_merkle(p2b_ctx* c, const u64* coeffs_d, u32 k, u64 P, u32 rate_bits, u32 cap_height,
+                          const u64* salt_d, u64* tmp, u64* leaves_d, u64 leaf_len, u64* digests_d, u64* cap_d,
+                          bool descending, cudaStream_t wait_before_block0) {
+  const u64 n = (u64)1 << k, R = (u64)1 << rate_bits, N = n << rate_bits;
+  const u32 log_N = k + rate_bits;
+  if (cap_height > log_N)
+    return fail(P2B_ERR_INVALID, "cap_height=%u should be at most log2(leaves.len())=%u", cap_height, log_N);
+  P2B_TRY(ensure_twiddles(c, log_N > 0 ? log_N - 1 : 0));
+  merkle::TreeShape shape = merkle::make_shape(log_N, cap_height);
+  ntt::LevelScale sc = lde_scale(k);
+  if (salt_d) {
+    scatter_salt_kernel<<<(unsigned)((N + 255) / 256), 256, 0, c->stream>>>(salt_d, N, log_N, leaves_d, leaf_len, P);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  // stream2 must not start hashing before earlier work on `stream` (salt scatter, previous users) is ordered
+  for (u64 i = 0; i < R; i++) {
+    u64 b = descending ? R - 1 - i : i;
+    if (b == 0 && wait_before_block0) CUDA_TRY(cudaStreamSynchronize(wait_before_block0));
+    P2B_TRY(run_lde_block(c, c->stream, coeffs_d, n, tmp, k, P, b, sc, leaves_d, leaf_len, 0));
+    // hash this block's rows on stream2 while the next block's NTT runs on stream
+    CUDA_TRY(cudaEventRecord(c->ev_a, c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->ev_a, 0));
+    P2B_TRY(launch_hash_leaves(c, c->stream2, leaves_d, leaf_len, 1, (u32)leaf_len, b * n, n, shape, digests_d, cap_d));
+  }
+  CUDA_TRY(cudaEventRecord(c->ev_b, c->stream2));
+  CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
+  P2B_TRY(launch_layers(c, c->stream, shape, digests_d, cap_d));
+  return P2B_OK;
+}
+
+static int commit_impl(p2b_ctx* c, const u64* input, int on_host, bool is_values, u32 k, u64 P, u32 rate_bits,
+                       u32 cap_height, const u64* salt, int salt_on_host, p2b_batch** out) {
+  if (!c || !out) return fail(P2B_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  if (!input || P == 0) return fail(P2B_ERR_INVALID, "empty batch (no polynomials)");
+  if (k + rate_bits > 32) return fail(P2B_ERR_INVALID, "degree_log + rate_bits = %u exceeds the field's two-adicity 32", k + rate_bits);
+  if (P > 65535) return fail(P2B_ERR_INVALID, "more than 65535 polynomials");
+  const u64 n = (u64)1 << k, N = n << rate_bits;
+  const u32 log_N = k + rate_bits;
+  if (cap_height > log_N)
+    return fail(P2B_ERR_INVALID, "cap_height=%u should be at most log2(leaves.len())=%u", cap_height, log_N);
+  CUDA_TRY(cudaSetDevice(c->device));
+  const u64 salt_size = salt ? P2B_SALT_SIZE : 0, leaf_len = P + salt_size;
+  const u64 ncap = (u64)1 << cap_height, ndig = 2 * (N - ncap);
+
+  p2b_batch* b = new (std::nothrow) p2b_batch();
+  if (!b) return fail(P2B_ERR_OOM, "host allocation failed");
+  b->ctx = c;
+  b->info = p2b_batch_info{k, rate_bits, cap_height, (u32)salt_size, P, N, leaf_len, ndig};
+  b->shape = merkle::make_shape(log_N, cap_height);
+  cudaStream_t st = c->stream;
+  u64* staged = nullptr;  // device copy of host input
+  u64* salt_d = nullptr;
+  int rc = P2B_OK;
+  auto body = [&]() -> int {
+    CUDA_TRY(cudaMallocAsync(&b->coeffs, P * n * sizeof(u64), st));
+    CUDA_TRY(cudaMallocAsync(&b->leaves, N * leaf_len * sizeof(u64), st));
+    CUDA_TRY(cudaMallocAsync(&b->digests, (ndig ? ndig : 1) * 4 * sizeof(u64), st));
+    CUDA_TRY(cudaMallocAsync(&b->cap, ncap * 4 * sizeof(u64), st));
+    P2B_TRY(ensure_scratch(c, P * n));
+    const u64* in_d = input;
+    if (on_host) {
+      // host input goes straight into the coefficient buffer (values are transformed in place there)
+      CUDA_TRY(cudaMemcpyAsync(b->coeffs, input, P * n * sizeof(u64), cudaMemcpyHostToDevice, st));
+      in_d = b->coeffs;
+    }
+    if (salt) {
+      if (salt_on_host) {
+        CUDA_TRY(cudaMallocAsync(&salt_d, P2B_SALT_SIZE * N * sizeof(u64), st));
+        CUDA_TRY(cudaMemcpyAsync(salt_d, salt, P2B_SALT_SIZE * N * sizeof(u64), cudaMemcpyHostToDevice, st));
+      } else {
+        salt_d = const_cast<u64*>(salt);
+      }
+    }
+    if (is_values) {
+      P2B_TRY(run_ifft(c, in_d, b->coeffs, c->scratch, k, P));
+    } else if (!on_host) {
+      CUDA_TRY(cudaMemcpyAsync(b->coeffs, input, P * n * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+    }
+    P2B_TRY(lde_and_merkle(c, b->coeffs, k, P, rate_bits, cap_height, salt_d, c->scratch, b->leaves, leaf_len,
+                           b->digests, b->cap, false, nullptr));
+    return P2B_OK;
+  };
+  rc = body();
+  if (salt_d && salt_on_host) cudaFreeAsync(salt_d, st);
+  if (staged) cudaFreeAsync(staged, st);
+  if (rc != P2B_OK) {
+    batch_free(b);
+    return rc;
+  }
+  *out = b;
+  return P2B_OK;
+}
+
+extern "C" int p2b_commit_from_values(p2b_ctx* ctx, const uint64_t* values, int values_on_host, uint32_t n_log,
+                                      uint64_t P, uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt,
+                                      int salt_on_host, p2b_batch** out) {
+  return commit_impl(ctx, values, values_on_host, true, n_log, P, rate_bits, cap_height, salt, salt_on_host, out);
+}
+extern "C" int p2b_commit_from_coeffs(p2b_ctx* ctx, const uint64_t* coeffs, int coeffs_on_host, uint32_t n_log,
+                                      uint64_t P, uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt,
+                                      int salt_on_host, p2b_batch** out) {
+  return commit_impl(ctx, coeffs, coeffs_on_host, false, n_log, P, rate_bits, cap_height, salt, salt_on_host, out);
+}
+
+extern "C" int p2b_batch_get_info(const p2b_batch* b, p2b_batch_info* out) {
+  if (!b || !out) return fail(P2B_ERR_INVALID, "NULL argument");
+  *out = b->info;
+  return P2B_OK;
+}
+extern "C" int p2b_batch_device_ptrs(const p2b_batch* b, uint64_t** coeffs, uint64_t** leaves, uint64_t** digests,
+                                     uint64_t** cap) {
+  if (!b) return fail(P2B_ERR_INVALID, "NULL batch");
+  if (coeffs) *coeffs = b->coeffs;
+  if (leaves) *leaves = b->leaves;
+  if (digests) *digests = b->digests;
+  if (cap) *cap = b->cap;
+  return P2B_OK;
+}
+
+static int d2h(const p2b_batch* b, void* dst, const void* src, size_t bytes) {
+  if (!dst) return fail(P2B_ERR_INVALID, "NULL output");
+  if (bytes == 0) return P2B_OK;
+  CUDA_TRY(cudaSetDevice(b->ctx->device));
+  CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, b->ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(b->ctx->stream));
+  return P2B_OK;
+}
+extern "C" int p2b_batch_get_coeffs(const p2b_batch* b, uint64_t* out) {
+  if (!b) return fail(P2B_ERR_INVALID, "NULL batch");
+  return d2h(b, out, b->coeffs, (b->info.num_polys << b->info.degree_log) * sizeof(u64));
+}
+extern "C" int p2b_batch_get_cap(const p2b_batch* b, uint64_t* out) {
+  if (!b) return fail(P2B_ERR_INVALID, "NULL batch");
+  return d2h(b, out, b->cap, ((size_t)4 << b->info.cap_height) * sizeof(u64));
+}
+extern "C" int p2b_batch_get_digests(const p2b_batch* b, uint64_t* out) {
+  if (!b) return fail(P2B_ERR_INVALID, "NULL batch");
+  return d2h(b, out, b->digests, b->info.num_digests * 4 * sizeof(u64));
+}
+extern "C" int p2b_batch_get_leaves(const p2b_batch* b, uint64_t first_leaf, uint64_t count, uint64_t* out) {
+  if (!b) return fail(P2B_ERR_INVALID, "NULL batch");
+  if (first_leaf + count > b->info.num_leaves) return fail(P2B_ERR_INVALID, "leaf range out of bounds");
+  return d2h(b, out, b->leaves + first_leaf * b->info.leaf_len, count * b->info.leaf_len * sizeof(u64));
+}
+extern "C" int p2b_batch_get_lde_values(const p2b_batch* b, uint64_t index, uint64_t step, uint64_t* out) {
+  if (!b) return fail(P2B_ERR_INVALID, "NULL batch");
+  u32 bits = b->info.degree_log + b->info.rate_bits;
+  u64 i = index * step;
+  if (i >= b->info.num_leaves) return fail(P2B_ERR_INVALID, "index*step out of the LDE domain");
+  u64 row = 0;
+  for (u32 t = 0; t < bits; t++) row |= ((i >> t) & 1) << (bits - 1 - t);  // reverse_bits, util/mod.rs:55-63
+  return d2h(b, out, b->leaves + row * b->info.leaf_len, b->info.num_polys * sizeof(u64));
+}
+
+// gather rows and/or Merkle paths for a list of leaf indices
+__global__ void open_rows_kernel(const u64* __restrict__ leaves, u64 leaf_len, const u64* __restrict__ digests,
+                                 merkle::TreeShape shape, const u64* __restrict__ idx, u64 count, u64* __restrict__ rows,
+                                 u64* __restrict__ sibs) {
+  u64 qi = blockIdx.x;
+  if (qi >= count) return;
+  u64 leaf = idx[qi];
+  if (rows)
+    for (u64 j = threadIdx.x; j < leaf_len; j += blockDim.x) rows[qi * leaf_len + j] = leaves[leaf * leaf_len + j];
+  if (sibs) {
+    // MerkleTree::prove, merkle_tree.rs:392-440
+    u32 layers = shape.sub_log;
+    u64 tree = leaf >> layers;
+    const u64* dt = digests + 4 * tree * shape.sub_digests;
+    for (u32 t = threadIdx.x; t < layers * 4; t += blockDim.x) {
+      u32 i = t >> 2, w = t & 3;
+      u64 pair_index = (leaf & (((u64)1 << layers) - 1)) >> i;
+      u64 parity = pair_index & 1;
+      pair_index >>= 1;
+      u64 siblings_index = (pair_index << (i + 1)) + ((u64)1 << i) - 1;
+      u64 sibling_index = 2 * siblings_index + (1 - parity);
+      sibs[(qi * layers + i) * 4 + w] = dt[4 * sibling_index + w];
+    }
+  }
+}
+
+static int open_impl(const p2b_batch* b, const u64* leaf_indices, u64 count, u64* rows_out, u64* sibs_out) {
+  if (!b || !leaf_indices) return fail(P2B_ERR_INVALID, "NULL argument");
+  if (count == 0) return P2B_OK;
+  for (u64 i = 0; i < count; i++)
+    if (leaf_indices[i] >= b->info.num_leaves) return fail(P2B_ERR_INVALID, "leaf index %llu out of range", (unsigned long long)leaf_indices[i]);
+  p2b_ctx* c = b->ctx;
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const u64 ll = b->info.leaf_len, layers = b->shape.sub_log;
+  u64 *d_idx = nullptr, *d_rows = nullptr, *d_sibs = nullptr;
+  auto body = [&]() -> int {
+    CUDA_TRY(cudaMallocAsync(&d_idx, count * sizeof(u64), st));
+    CUDA_TRY(cudaMemcpyAsync(d_idx, leaf_indices, count * sizeof(u64), cudaMemcpyHostToDevice, st));
+    if (rows_out) CUDA_TRY(cudaMallocAsync(&d_rows, count * ll * sizeof(u64), st));
+    if (sibs_out && layers) CUDA_TRY(cudaMallocAsync(&d_sibs, count * layers * 4 * sizeof(u64), st));
+    open_rows_kernel<<<(unsigned)count, 128, 0, st>>>(b->leaves, ll, b->digests, b->shape, d_idx, count, d_rows, d_sibs);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (d_rows) CUDA_TRY(cudaMemcpyAsync(rows_out, d_rows, count * ll * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    if (d_sibs) CUDA_TRY(cudaMemcpyAsync(sibs_out, d_sibs, count * layers * 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return P2B_OK;
+  };
+  int rc = body();
+  if (d_idx) cudaFreeAsync(d_idx, st);
+  if (d_rows) cudaFreeAsync(d_rows, st);
+  if (d_sibs) cudaFreeAsync(d_sibs, st);
+  return rc;
+}
+extern "C" int p2b_batch_prove(const p2b_batch* b, const uint64_t* leaf_indices, uint64_t count, uint64_t* siblings_out) {
+  if (!siblings_out && b && b->shape.sub_log) return fail(P2B_ERR_INVALID, "NULL output");
+  return open_impl(b, leaf_indices, count, nullptr, siblings_out);
+}
+extern "C" int p2b_batch_open_rows(const p2b_batch* b, const uint64_t* leaf_indices, uint64_t count, uint64_t* rows_out,
+                                   uint64_t* siblings_out) {
+  if (!rows_out) return fail(P2B_ERR_INVALID, "NULL output");
+  return open_impl(b, leaf_indices, count, rows_out, siblings_out);
+}
+
+// ======================================================================================================
+// building blocks
+// ======================================================================================================
+extern "C" int p2b_ifft_batch(p2b_ctx* c, const uint64_t* d_src, uint64_t* d_dst, uint32_t n_log, uint64_t P) {
+  if (!c || !d_src || !d_dst) return fail(P2B_ERR_INVALID, "NULL argument");
+  if (n_log > 32) return fail(P2B_ERR_INVALID, "n_log exceeds two-adicity");
+  if (P > 65535) return fail(P2B_ERR_INVALID, "more than 65535 polynomials");
+  CUDA_TRY(cudaSetDevice(c->device));
+  Plan pl = make_plan(n_log);
+  u64* tmp = d_dst;
+  if (pl.n_strided) {
+    P2B_TRY(ensure_scratch(c, P << n_log));
+    tmp = c->scratch;
+  }
+  return run_ifft(c, d_src, d_dst, tmp, n_log, P);
+}
+
+extern "C" int p2b_lde_leaves(p2b_ctx* c, const uint64_t* d_coeffs, uint32_t n_log, uint64_t P, uint32_t rate_bits,
+                              uint64_t* d_leaves, uint64_t row_stride, uint64_t col0) {
+  if (!c || !d_coeffs || !d_leaves) return fail(P2B_ERR_INVALID, "NULL argument");
+  if (n_log + rate_bits > 32) return fail(P2B_ERR_INVALID, "degree_log + rate_bits exceeds two-adicity");
+  if (P > 65535) return fail(P2B_ERR_INVALID, "more than 65535 polynomials");
+  if (col0 + P > row_stride) return fail(P2B_ERR_INVALID, "columns do not fit the row stride");
+  CUDA_TRY(cudaSetDevice(c->device));
+  u32 log_N = n_log + rate_bits;
+  P2B_TRY(ensure_twiddles(c, log_N > 0 ? log_N - 1 : 0));
+  P2B_TRY(ensure_scratch(c, P << n_log));
+  ntt::LevelScale sc = lde_scale(n_log);
+  for (u64 b = 0; b < ((u64)1 << rate_bits); b++)
+    P2B_TRY(run_lde_block(c, c->stream, d_coeffs, (u64)1 << n_log, c->scratch, n_log, P, b, sc, d_leaves, row_stride, col0));
+  return P2B_OK;
+}
+
+extern "C" int p2b_merkle_tree(p2b_ctx* c, const uint64_t* d_leaves, uint64_t num_leaves, uint64_t leaf_len,
+                               uint64_t row_stride, uint64_t col_stride, uint32_t cap_height, uint64_t* d_digests,
+                               uint64_t* d_cap) {
+  if (!c || !d_leaves || !d_cap) return fail(P2B_ERR_INVALID, "NULL argument");
+  if (num_leaves == 0 || (num_leaves & (num_leaves - 1))) return fail(P2B_ERR_INVALID, "number of leaves must be a power of two");
+  u32 lg = 0;
+  while (((u64)1 << lg) < num_leaves) lg++;
+  if (cap_height > lg) return fail(P2B_ERR_INVALID, "cap_height=%u should be at most log2(leaves.len())=%u", cap_height, lg);
+  if (cap_height < lg && !d_digests) return fail(P2B_ERR_INVALID, "NULL digests");
+  if (leaf_len > 0xffffffffull) return fail(P2B_ERR_INVALID, "leaf too long");
+  CUDA_TRY(cudaSetDevice(c->device));
+  merkle::TreeShape shape = merkle::make_shape(lg, cap_height);
+  P2B_TRY(launch_hash_leaves(c, c->stream, d_leaves, row_stride, col_stride, (u32)leaf_len, 0, num_leaves, shape, d_digests, d_cap));
+  return launch_layers(c, c->stream, shape, d_digests, d_cap);
+}
+
+extern "C" int p2b_poseidon_permute(p2b_ctx* c, uint64_t* d_states, uint64_t count) {
+  if (!c || !d_states) return fail(P2B_ERR_INVALID, "NULL argument");
+  if (count == 0) return P2B_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  merkle::permute_kernel<<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(d_states, count, 1);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return P2B_OK;
+}
+
+__global__ void field_op_kernel(int op, const u64* __restrict__ a, const u64* __restrict__ b, u64* __restrict__ out, u64 count) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  u64 x = a[i], y = b[i], r;
+  switch (op) {
+    case 0: r = gl::add(x, y); break;
+    case 1: r = gl::sub(x, y); break;
+    case 2: r = gl::mul(x, y); break;
+    case 3: r = gl::mul_add(x, y, x); break;       // x*y + x
+    case 4: r = gl::add_canonical(x, gl::canon(y)); break;
+    case 5: r = gl::sub_canonical(x, gl::canon(y)); break;
+    default: r = 0;
+  }
+  out[i] = gl::canon(r);
+}
+extern "C" int p2b_field_op(p2b_ctx* c, int op, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, uint64_t count) {
+  if (!c || !d_a || !d_b || !d_out) return fail(P2B_ERR_INVALID, "NULL argument");
+  if (op < 0 || op > 5) return fail(P2B_ERR_INVALID, "unknown op %d", op);
+  if (count == 0) return P2B_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  field_op_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(op, d_a, d_b, d_out, count);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return P2B_OK;
+}
+
+// splitmix64(seed + index) with rejection of values >= p (re-mix until canonical), BASELINE.md C2
+__host__ __device__ static inline u64 splitmix64(u64 x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__global__ void fill_synthetic_kernel(u64* __restrict__ out, u64 count, u64 seed, u64 first) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  u64 v = splitmix64(seed ^ splitmix64(first + i));
+  while (v >= gl::P) v = splitmix64(v);
+  out[i] = v;
+}
+extern "C" int p2b_fill_synthetic(p2b_ctx* c, uint64_t* d_out, uint64_t count, uint64_t seed, uint64_t first_index) {
+  if (!c || !d_out) return fail(P2B_ERR_INVALID, "NULL argument");
+  if (count == 0) return P2B_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  fill_synthetic_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(d_out, count, seed, first_index);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return P2B_OK;
+}
+
+extern "C" int p2b_malloc(p2b_ctx* c, uint64_t bytes, void** out) {
+  if (!c || !out) return fail(P2B_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMalloc(out, bytes ? bytes : 1));
+  return P2B_OK;
+}
+extern "C" int p2b_free(p2b_ctx* c, void* ptr) {
+  if (!c) return fail(P2B_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaFree(ptr));
+  return P2B_OK;
+}
+extern "C" int p2b_malloc_host(uint64_t bytes, void** out) {
+  if (!out) return fail(P2B_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaMallocHost(out, bytes ? bytes : 1));
+  return P2B_OK;
+}
+extern "C" int p2b_free_host(void* ptr) {
+  CUDA_TRY(cudaFreeHost(ptr));
+  return P2B_OK;
+}
+extern "C" int p2b_memcpy_h2d(p2b_ctx* c, void* d_dst, const void* h_src, uint64_t bytes) {
+  if (!c) return fail(P2B_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return P2B_OK;
+}
+extern "C" int p2b_memcpy_d2h(p2b_ctx* c, void* h_dst, const void* d_src, uint64_t bytes) {
+  if (!c) return fail(P2B_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return P2B_OK;
+}
+extern "C" int p2b_timer_start(p2b_ctx* c) {
+  if (!c) return fail(P2B_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaEventRecord(c->ev_t0, c->stream));
+  return P2B_OK;
+}
+extern "C" int p2b_timer_stop_ms(p2b_ctx* c, float* ms_out) {
+  if (!c || !ms_out) return fail(P2B_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaEventRecord(c->ev_t1, c->stream));
+  CUDA_TRY(cudaEventSynchronize(c->ev_t1));
+  CUDA_TRY(cudaEventElapsedTime(ms_out, c->ev_t0, c->ev_t1));
+  return P2B_OK;
+}
+
+#include "compat.cuh"

@@ -1,0 +1,205 @@
+// poseidon.cuh -- Poseidon permutation over Goldilocks (width 12, x^7, 4 + 22 + 4 rounds) and the
+// overwrite-mode sponge / 2-to-1 compression built on it, for sm_100a.
+//
+// What is computed (bit-exact with the reference CPU path):
+//   permute()        Poseidon::poseidon            plonky2/src/hash/poseidon.rs:590-606
+//   full round       constant_layer/sbox/mds_layer poseidon.rs:482-493, 525-548, 172-260
+//   partial rounds   "fast" form                   poseidon.rs:574-588 with :310-365 (first-round constants +
+//                                                  11x11 initial matrix) and :398-427 (W_HATS / VS layer)
+//   hash_or_noop / hash_no_pad / two_to_one        plonk/config.rs:56-67, hash/hashing.rs:81-104, :65-72
+//
+// How (B200): the 12-word state lives in registers (24 x 32-bit); a full round's MDS works on the 32-bit
+// halves of each word with IMAD.WIDE.U32 multiply-accumulates by the <=6-bit circulant entries (immediates
+// in the instruction stream), sums both halves in 64-bit accumulators (no carries possible: 12 * 41 * 2^32
+// < 2^42), adds the NEXT round's constant into the 96-bit sum and reduces once.  S-boxes are 4 mod-muls of
+// gl::mul (4 IMAD.WIDE + reduce).  Round loops are kept rolled (#pragma unroll 1) so the hot loop bodies
+// (~1.2k instructions for a full round, ~0.5k for a partial round) stay inside the instruction cache;
+// per-round constants are fetched from __constant__ memory (uniform across the warp -> LDC broadcast).
+#pragma once
+#include "gl64.cuh"
+#include "poseidon_tables.h"
+
+namespace poseidon {
+
+using gl::u32;
+using gl::u64;
+
+// __constant__ copies (filled by poseidon_upload_constants()).
+struct Consts {
+  u64 rc[360];        // ALL_ROUND_CONSTANTS
+  u64 first_rc[12];   // FAST_PARTIAL_FIRST_ROUND_CONSTANT
+  u64 partial_rc[22]; // FAST_PARTIAL_ROUND_CONSTANTS
+  u64 vs[22 * 11];    // FAST_PARTIAL_ROUND_VS
+  u64 w_hats[22 * 11];// FAST_PARTIAL_ROUND_W_HATS
+  u64 init[11 * 11];  // FAST_PARTIAL_ROUND_INITIAL_MATRIX  [r-1][c-1]
+  u64 post[8 * 12];   // constants added right after the MDS of full round k (k = 0..7): rows 1,2,3 of rc,
+                      // first_rc, rows 27,28,29 of rc, zeros  (next round's constant_layer folded forward)
+};
+// The library is a single translation unit (plonky2_b200.cu), so the definition lives here.
+__constant__ Consts C;
+
+// MDS circulant first row and diagonal (poseidon_goldilocks.rs:21-22) as compile-time immediates.
+__device__ __forceinline__ constexpr u32 mds_circ(int i) {
+  constexpr u32 t[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+  return t[i];
+}
+static constexpr u32 MDS_DIAG0 = 8;
+
+// x^7 (sbox_monomial, poseidon.rs:525-532)
+__device__ __forceinline__ u64 sbox(u64 x) {
+  u64 x2 = gl::sqr(x);
+  u64 x4 = gl::sqr(x2);
+  u64 x3 = gl::mul(x, x2);
+  return gl::mul(x3, x4);
+}
+
+// out[r] = sum_i circ[i] * s[(i+r)%12] + diag[r]*s[r] + addc[r]   (mds_row_shf + mds_layer, then the next
+// constant_layer folded in).  addc must be canonical round constants (< p).
+__device__ __forceinline__ void mds_layer(u64 (&s)[12], const u64* __restrict__ addc) {
+  u32 lo[12], hi[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) gl::split(s[i], lo[i], hi[i]);
+#pragma unroll
+  for (int r = 0; r < 12; r++) {
+    u64 al = 0, ah = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      al += (u64)lo[(i + r) % 12] * mds_circ(i);
+      ah += (u64)hi[(i + r) % 12] * mds_circ(i);
+    }
+    if (r == 0) {
+      al += (u64)lo[0] * MDS_DIAG0;
+      ah += (u64)hi[0] * MDS_DIAG0;
+    }
+    // value = al + ah * 2^32 (+ addc)  as (w0, w1, w2) 32-bit limbs -> 96 bits
+    u32 al0, al1, ah0, ah1, w0, w1, w2;
+    gl::split(al, al0, al1);
+    gl::split(ah, ah0, ah1);
+    {
+      u32 c0, c1;
+      gl::split(addc[r], c0, c1);
+      asm("{\n\t"
+          "add.cc.u32 %1, %4, %5;\n\t"
+          "addc.u32 %2, %6, 0;\n\t"
+          "add.cc.u32 %0, %3, %7;\n\t"
+          "addc.cc.u32 %1, %1, %8;\n\t"
+          "addc.u32 %2, %2, 0;\n\t"
+          "}"
+          : "=&r"(w0), "=&r"(w1), "=&r"(w2)
+          : "r"(al0), "r"(al1), "r"(ah0), "r"(ah1), "r"(c0), "r"(c1));
+    }
+    s[r] = gl::reduce96(gl::pack(w0, w1), w2);
+  }
+}
+
+// 128-bit accumulate helper for the partial-round dot products: (acc_lo, acc_hi, acc_top) += a*b
+__device__ __forceinline__ void mac160(u64& lo, u64& hi, u32& top, u64 a, u64 b) {
+  u64 pl, ph;
+  gl::mul_wide(a, b, pl, ph);
+  asm("{ add.cc.u64 %0, %0, %3; addc.cc.u64 %1, %1, %4; addc.u32 %2, %2, 0; }" : "+l"(lo), "+l"(hi), "+r"(top) : "l"(pl), "l"(ph));
+}
+// reduce_u160 (poseidon.rs:40-47)
+__device__ __forceinline__ u64 reduce160(u64 lo, u64 hi, u32 top) {
+  u64 reduced_hi = gl::reduce96(hi, top);
+  return gl::reduce128(lo, reduced_hi);
+}
+
+// The permutation.  Input: any u64 representatives; output: u64 representatives (NOT canonicalised --
+// callers canonicalise what they store).
+__device__ __forceinline__ void permute(u64 (&s)[12]) {
+  // constant layer of round 0 up front; every later constant layer is folded into the preceding MDS.
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = gl::add_canonical(s[i], C.rc[i]);
+#pragma unroll 1
+  for (int half = 0; half < 2; half++) {
+    // ---- 4 full rounds (poseidon.rs:560-572) ----
+#pragma unroll 1
+    for (int r = 0; r < 4; r++) {
+#pragma unroll
+      for (int i = 0; i < 12; i++) s[i] = sbox(s[i]);
+      mds_layer(s, &C.post[12 * (half * 4 + r)]);
+    }
+    if (half == 0) {
+      // ---- partial rounds (poseidon.rs:574-588); first-round constants were folded into post[3] ----
+      {
+        // mds_partial_layer_init (poseidon.rs:310-337): t[0] = s[0]; t[c] = sum_r s[r] * init[r-1][c-1]
+        u64 t[12];
+        t[0] = s[0];
+#pragma unroll
+        for (int c = 1; c < 12; c++) {
+          u64 lo = 0, hi = 0;
+          u32 top = 0;
+#pragma unroll
+          for (int r = 1; r < 12; r++) mac160(lo, hi, top, s[r], C.init[(r - 1) * 11 + (c - 1)]);
+          t[c] = reduce160(lo, hi, top);
+        }
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = t[i];
+      }
+#pragma unroll 1
+      for (int r = 0; r < 22; r++) {
+        u64 s0 = gl::add_canonical(sbox(s[0]), C.partial_rc[r]);
+        // mds_partial_layer_fast (poseidon.rs:398-427): d = 25*s0 + sum w_hat[i-1]*s[i]  (u160 accumulator)
+        u64 lo, hi;
+        u32 top = 0;
+        {
+          u32 a0, a1;
+          gl::split(s0, a0, a1);
+          u64 pl = (u64)a0 * (mds_circ(0) + MDS_DIAG0), ph = (u64)a1 * (mds_circ(0) + MDS_DIAG0);
+          u32 pl0, pl1, ph0, ph1, m1, m2;
+          gl::split(pl, pl0, pl1);
+          gl::split(ph, ph0, ph1);
+          asm("{ add.cc.u32 %0, %2, %3; addc.u32 %1, %4, 0; }" : "=&r"(m1), "=&r"(m2) : "r"(pl1), "r"(ph0), "r"(ph1));
+          lo = gl::pack(pl0, m1);
+          hi = (u64)m2;
+        }
+#pragma unroll
+        for (int i = 1; i < 12; i++) mac160(lo, hi, top, s[i], C.w_hats[r * 11 + i - 1]);
+        u64 d = reduce160(lo, hi, top);
+#pragma unroll
+        for (int i = 1; i < 12; i++) s[i] = gl::mul_add(s0, C.vs[r * 11 + i - 1], s[i]);
+        s[0] = d;
+      }
+      // constant layer of round 26 (first of the closing full rounds)
+#pragma unroll
+      for (int i = 0; i < 12; i++) s[i] = gl::add_canonical(s[i], C.rc[12 * 26 + i]);
+    }
+  }
+}
+
+// compress / two_to_one (hashing.rs:65-72): perm([l, r, 0,0,0,0])[0..4]; output canonical.
+__device__ __forceinline__ void two_to_one(const u64 l[4], const u64 r[4], u64 out[4]) {
+  u64 s[12];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    s[i] = l[i];
+    s[4 + i] = r[i];
+    s[8 + i] = 0;
+  }
+  permute(s);
+#pragma unroll
+  for (int i = 0; i < 4; i++) out[i] = gl::canon(s[i]);
+}
+
+// host: copy the tables into __constant__ memory of the current device
+inline cudaError_t upload_constants() {
+  static Consts h;
+  for (int i = 0; i < 360; i++) h.rc[i] = P2_ROUND_CONSTANTS[i];
+  for (int i = 0; i < 12; i++) h.first_rc[i] = P2_PARTIAL_FIRST_RC[i];
+  for (int i = 0; i < 22; i++) h.partial_rc[i] = P2_PARTIAL_RC[i];
+  for (int i = 0; i < 242; i++) h.vs[i] = P2_PARTIAL_VS[i];
+  for (int i = 0; i < 242; i++) h.w_hats[i] = P2_PARTIAL_W_HATS[i];
+  for (int i = 0; i < 121; i++) h.init[i] = P2_PARTIAL_INIT_MATRIX[i];
+  for (int k = 0; k < 8; k++)
+    for (int i = 0; i < 12; i++) {
+      u64 v;
+      if (k < 3) v = P2_ROUND_CONSTANTS[12 * (k + 1) + i];
+      else if (k == 3) v = P2_PARTIAL_FIRST_RC[i];
+      else if (k < 7) v = P2_ROUND_CONSTANTS[12 * (26 + (k - 4) + 1) + i];
+      else v = 0;
+      h.post[12 * k + i] = v;
+    }
+  return cudaMemcpyToSymbol(C, &h, sizeof(h));
+}
+
+}  // namespace poseidon
