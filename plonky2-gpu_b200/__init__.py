@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libplonky2_b200.so")
+LIB_PATH = os.environ.get("P2B_LIB") or os.path.join(_HERE, "libplonky2_b200.so")  # P2B_LIB: experimental variants only
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "plonky2_b200.h")
 ORDER = 0xFFFFFFFF00000001
 SALT_SIZE = 4
@@ -36,6 +36,8 @@ def _load_build_module():
 
 def build(force=False, verbose=False):
     """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    if os.environ.get("P2B_LIB"):
+        return LIB_PATH
     return _load_build_module().build(force=force, verbose=verbose)
 
 

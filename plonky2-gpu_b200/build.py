@@ -37,12 +37,14 @@ def needs_build():
     return False
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: build an experimental variant (tools/variants.py) next to the product library."""
+    so = out or SO
+    if out is None and not force and not needs_build():
         return SO
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
            "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v" if verbose else "-O3",
-           "-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-o", so] + ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES]
     # the host compiler of this image's CC/CXX env may lack its specs; use the system one
     if os.path.exists("/usr/bin/g++"):
         cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
@@ -51,7 +53,7 @@ def build(force=False, verbose=False):
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libplonky2_b200.so")
-    return SO
+    return so
 
 
 if __name__ == "__main__":

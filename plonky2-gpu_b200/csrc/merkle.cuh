@@ -72,19 +72,15 @@ __device__ __forceinline__ void hash_leaf(const u64* __restrict__ base, u64 col_
   u64 s[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = 0;
-  u32 full = leaf_len / 8, rem = leaf_len % 8;
+  // one loop for full and partial chunks (a second inlined copy of the permutation would double the code size);
+  // the partial last chunk overwrites only `leaf_len % 8` lanes (hashing.rs:88-91)
   const u64* p = base;
 #pragma unroll 1
-  for (u32 k = 0; k < full; k++) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) s[i] = __ldg(p + i * col_stride);
-    p += 8 * col_stride;
-    poseidon::permute(s);
-  }
-  if (rem) {  // partial last chunk overwrites only `rem` lanes (hashing.rs:88-91)
+  for (u32 left = leaf_len; left > 0; left = left > 8 ? left - 8 : 0) {
 #pragma unroll
     for (int i = 0; i < 8; i++)
-      if ((u32)i < rem) s[i] = __ldg(p + i * col_stride);
+      if ((u32)i < left) s[i] = __ldg(p + i * col_stride);
+    p += 8 * col_stride;
     poseidon::permute(s);
   }
 #pragma unroll
@@ -94,40 +90,48 @@ __device__ __forceinline__ void hash_leaf(const u64* __restrict__ base, u64 col_
 // One thread per leaf.  leaves element (row, col) at leaves[row * row_stride + col * col_stride].
 // leaf_index0: global index of this launch's first leaf (multi-GPU shards / coset blocks hash a sub-range
 // of the tree's leaves but write into the whole tree's layout).
-__global__ void __launch_bounds__(128)
+#ifndef P2B_HASH_BLOCK
+#define P2B_HASH_BLOCK 128
+#endif
+__global__ void __launch_bounds__(P2B_HASH_BLOCK)
 hash_leaves_kernel(const u64* __restrict__ leaves, u64 row_stride, u64 col_stride, u32 leaf_len, u64 count,
                    u64 leaf_index0, TreeShape shape, u64* __restrict__ digests, u64* __restrict__ cap) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
+  // tail threads stay alive on a clamped index (they may take part in block-wide barriers inside permute)
+  const bool live = i < count;
+  if (!live) i = count - 1;
   u64 h[4];
   hash_leaf(leaves + i * row_stride, col_stride, leaf_len, h);
-  store_hash(node_slot(shape, digests, cap, 0, leaf_index0 + i), h);
+  if (live) store_hash(node_slot(shape, digests, cap, 0, leaf_index0 + i), h);
 }
 
 // One thread per node of layer `l` (l >= 1): parent of nodes 2Q, 2Q+1 of layer l-1.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(P2B_HASH_BLOCK)
 merkle_layer_kernel(TreeShape shape, u32 l, u64 node0, u64 count, u64* __restrict__ digests, u64* __restrict__ cap) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
+  const bool live = i < count;
+  if (!live) i = count - 1;
   u64 Q = node0 + i;
   const u64* left = node_slot(shape, digests, cap, l - 1, 2 * Q);  // siblings are adjacent: left + 4
   u64 a[4], b[4], h[4];
   load_hash(left, a);
   load_hash(left + 4, b);
   poseidon::two_to_one(a, b, h);
-  store_hash(node_slot(shape, digests, cap, l, Q), h);
+  if (live) store_hash(node_slot(shape, digests, cap, l, Q), h);
 }
 
 // Batched permutation (test / micro-benchmark entry): states[i][12] -> permuted, canonical.
-__global__ void __launch_bounds__(128) permute_kernel(u64* __restrict__ states, u64 count, int reps) {
+__global__ void __launch_bounds__(P2B_HASH_BLOCK) permute_kernel(u64* __restrict__ states, u64 count, int reps) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
+  const bool live = i < count;
+  if (!live) i = count - 1;
   u64 s[12];
 #pragma unroll
   for (int k = 0; k < 12; k++) s[k] = states[i * 12 + k];
   for (int r = 0; r < reps; r++) poseidon::permute(s);
 #pragma unroll
-  for (int k = 0; k < 12; k++) states[i * 12 + k] = gl::canon(s[k]);
+  for (int k = 0; k < 12; k++)
+    if (live) states[i * 12 + k] = gl::canon(s[k]);
 }
 
 }  // namespace merkle

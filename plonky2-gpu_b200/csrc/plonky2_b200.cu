@@ -389,8 +389,8 @@ static int launch_hash_leaves(p2b_ctx* c, cudaStream_t st, const u64* leaves, u6
                               u32 leaf_len, u64 first_leaf, u64 count, const merkle::TreeShape& shape, u64* digests,
                               u64* cap) {
   if (count == 0) return P2B_OK;
-  unsigned blocks = (unsigned)((count + 127) / 128);
-  merkle::hash_leaves_kernel<<<blocks, 128, 0, st>>>(leaves + first_leaf * row_stride, row_stride, col_stride, leaf_len,
+  unsigned blocks = (unsigned)((count + P2B_HASH_BLOCK - 1) / P2B_HASH_BLOCK);
+  merkle::hash_leaves_kernel<<<blocks, P2B_HASH_BLOCK, 0, st>>>(leaves + first_leaf * row_stride, row_stride, col_stride, leaf_len,
                                                      count, first_leaf, shape, digests, cap);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -399,8 +399,8 @@ static int launch_hash_leaves(p2b_ctx* c, cudaStream_t st, const u64* leaves, u6
 static int launch_layers(p2b_ctx* c, cudaStream_t st, const merkle::TreeShape& shape, u64* digests, u64* cap) {
   for (u32 l = 1; l <= shape.sub_log; l++) {
     u64 count = shape.num_leaves >> l;
-    unsigned blocks = (unsigned)((count + 127) / 128);
-    merkle::merkle_layer_kernel<<<blocks, 128, 0, st>>>(shape, l, 0, count, digests, cap);
+    unsigned blocks = (unsigned)((count + P2B_HASH_BLOCK - 1) / P2B_HASH_BLOCK);
+    merkle::merkle_layer_kernel<<<blocks, P2B_HASH_BLOCK, 0, st>>>(shape, l, 0, count, digests, cap);
     c->launches++;
   }
   CUDA_TRY(cudaGetLastError());
@@ -719,7 +719,7 @@ extern "C" int p2b_poseidon_permute(p2b_ctx* c, uint64_t* d_states, uint64_t cou
   if (!c || !d_states) return fail(P2B_ERR_INVALID, "NULL argument");
   if (count == 0) return P2B_OK;
   CUDA_TRY(cudaSetDevice(c->device));
-  merkle::permute_kernel<<<(unsigned)((count + 127) / 128), 128, 0, c->stream>>>(d_states, count, 1);
+  merkle::permute_kernel<<<(unsigned)((count + P2B_HASH_BLOCK - 1) / P2B_HASH_BLOCK), P2B_HASH_BLOCK, 0, c->stream>>>(d_states, count, 1);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   return P2B_OK;

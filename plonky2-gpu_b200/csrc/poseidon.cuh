@@ -56,6 +56,50 @@ __device__ __forceinline__ u64 sbox(u64 x) {
 // out[r] = sum_i circ[i] * s[(i+r)%12] + diag[r]*s[r] + addc[r]   (mds_row_shf + mds_layer, then the next
 // constant_layer folded in).  addc must be canonical round constants (< p).
 __device__ __forceinline__ void mds_layer(u64 (&s)[12], const u64* __restrict__ addc) {
+#ifdef P2B_MDS_LIMB22
+  // Three 22/22/20-bit limbs per word: every product c*limb and every 12-term sum stays below 2^32, so the whole
+  // layer is 32-bit IMAD (64 thread-instr/clk/SM) instead of IMAD.WIDE (~23): 432 IMAD vs 288 IMAD.WIDE.
+  u32 x0[12], x1[12], x2[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    u32 lo, hi;
+    gl::split(s[i], lo, hi);
+    x0[i] = lo & 0x3fffffu;
+    x1[i] = __funnelshift_r(lo, hi, 22) & 0x3fffffu;
+    x2[i] = hi >> 12;
+  }
+#pragma unroll
+  for (int r = 0; r < 12; r++) {
+    u32 s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      s0 += x0[(i + r) % 12] * mds_circ(i);
+      s1 += x1[(i + r) % 12] * mds_circ(i);
+      s2 += x2[(i + r) % 12] * mds_circ(i);
+    }
+    if (r == 0) {
+      s0 += x0[0] * MDS_DIAG0;
+      s1 += x1[0] * MDS_DIAG0;
+      s2 += x2[0] * MDS_DIAG0;
+    }
+    // value = s0 + s1*2^22 + s2*2^44 + addc[r]  ->  (w0, w1, w2)
+    u32 c0, c1, w0, w1, w2;
+    gl::split(addc[r], c0, c1);
+    u32 a_lo = s1 << 22, a_hi = s1 >> 10;   // s1 * 2^22 as (lo, hi)
+    u32 b_lo = s2 << 12, b_hi = s2 >> 20;   // s2 * 2^44 as (mid, top)
+    asm("{\n\t"
+        "add.cc.u32 %0, %3, %4;\n\t"        // w0 = s0 + a_lo
+        "addc.cc.u32 %1, %5, %6;\n\t"       // w1 = a_hi + b_lo + c
+        "addc.u32 %2, %7, 0;\n\t"           // w2 = b_hi + c
+        "add.cc.u32 %0, %0, %8;\n\t"        // + round constant
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.u32 %2, %2, 0;\n\t"
+        "}"
+        : "=&r"(w0), "=&r"(w1), "=&r"(w2)
+        : "r"(s0), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(c0), "r"(c1));
+    s[r] = gl::reduce96(gl::pack(w0, w1), w2);
+  }
+#else
   u32 lo[12], hi[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) gl::split(s[i], lo[i], hi[i]);
@@ -90,6 +134,29 @@ __device__ __forceinline__ void mds_layer(u64 (&s)[12], const u64* __restrict__ 
     }
     s[r] = gl::reduce96(gl::pack(w0, w1), w2);
   }
+#endif
+}
+
+// sbox_layer (poseidon.rs:534-548).  Code size matters more than instruction count here: with ~28 warps per SM
+// streaming through the permutation, instruction fetch stalls ("no_instruction" in ncu) dominate as soon as the
+// hot code exceeds the ~32 KB instruction cache, so the 12 S-boxes are a rolled loop of 3 x 4 with a register
+// rotation (24 moves per iteration) instead of 12 inlined copies (13 KB of SASS).
+__device__ __forceinline__ void sbox_layer(u64 (&s)[12]) {
+#ifdef P2B_SBOX_UNROLLED
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = sbox(s[i]);
+#else
+#pragma unroll 1
+  for (int g = 0; g < 3; g++) {
+    u64 t0 = sbox(s[0]), t1 = sbox(s[1]), t2 = sbox(s[2]), t3 = sbox(s[3]);
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = s[i + 4];
+    s[8] = t0;
+    s[9] = t1;
+    s[10] = t2;
+    s[11] = t3;
+  }
+#endif
 }
 
 // 128-bit accumulate helper for the partial-round dot products: (acc_lo, acc_hi, acc_top) += a*b
@@ -104,6 +171,16 @@ __device__ __forceinline__ u64 reduce160(u64 lo, u64 hi, u32 top) {
   return gl::reduce128(lo, reduced_hi);
 }
 
+// Optional block-wide barrier at every round boundary (P2B_SYNC_ROUNDS): keeps all warps of a CTA inside the same
+// loop body so they share instruction-cache lines (the unrolled round bodies are 8-20 KB each and ncu shows
+// "no_instruction" as the top stall when warps drift apart).  Only legal when every thread of the CTA runs the
+// same number of permutations -- the kernels that enable it keep their tail threads alive on clamped indices.
+__device__ __forceinline__ void round_sync() {
+#ifdef P2B_SYNC_ROUNDS
+  __syncthreads();
+#endif
+}
+
 // The permutation.  Input: any u64 representatives; output: u64 representatives (NOT canonicalised --
 // callers canonicalise what they store).
 __device__ __forceinline__ void permute(u64 (&s)[12]) {
@@ -115,14 +192,15 @@ __device__ __forceinline__ void permute(u64 (&s)[12]) {
     // ---- 4 full rounds (poseidon.rs:560-572) ----
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
-#pragma unroll
-      for (int i = 0; i < 12; i++) s[i] = sbox(s[i]);
+      round_sync();
+      sbox_layer(s);
       mds_layer(s, &C.post[12 * (half * 4 + r)]);
     }
     if (half == 0) {
       // ---- partial rounds (poseidon.rs:574-588); first-round constants were folded into post[3] ----
       {
         // mds_partial_layer_init (poseidon.rs:310-337): t[0] = s[0]; t[c] = sum_r s[r] * init[r-1][c-1]
+#ifdef P2B_INIT_UNROLLED
         u64 t[12];
         t[0] = s[0];
 #pragma unroll
@@ -135,9 +213,30 @@ __device__ __forceinline__ void permute(u64 (&s)[12]) {
         }
 #pragma unroll
         for (int i = 0; i < 12; i++) s[i] = t[i];
+#else
+        // rolled over the output column c (keeps ~24 KB of straight-line code out of the instruction cache); the
+        // results are pushed through a shift register so no register array is indexed dynamically.
+        u64 t[12];
+#pragma unroll
+        for (int i = 1; i < 12; i++) t[i] = 0;
+#pragma unroll 1
+        for (int c = 0; c < 11; c++) {
+          u64 lo = 0, hi = 0;
+          u32 top = 0;
+#pragma unroll
+          for (int r = 1; r < 12; r++) mac160(lo, hi, top, s[r], C.init[(r - 1) * 11 + c]);
+          u64 v = reduce160(lo, hi, top);
+#pragma unroll
+          for (int i = 1; i < 11; i++) t[i] = t[i + 1];
+          t[11] = v;
+        }
+#pragma unroll
+        for (int i = 1; i < 12; i++) s[i] = t[i];
+#endif
       }
 #pragma unroll 1
       for (int r = 0; r < 22; r++) {
+        round_sync();
         u64 s0 = gl::add_canonical(sbox(s[0]), C.partial_rc[r]);
         // mds_partial_layer_fast (poseidon.rs:398-427): d = 25*s0 + sum w_hat[i-1]*s[i]  (u160 accumulator)
         u64 lo, hi;
