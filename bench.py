@@ -1,0 +1,356 @@
+#!/usr/bin/env python3
+"""bench.py -- LDE + Merkle commit (PolynomialBatch::from_values) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        # the reference's CPU algorithm (oracle port) on the host cores
+
+Workload (BASELINE.json configs[1]): 2^20 rows x 135 Goldilocks columns, rate_bits = 3, cap_height = 4, Poseidon
+Merkle tree, no blinding; synthetic values from splitmix64.  A step is one commit of that matrix:
+batched inverse NTT -> coset LDE in leaf order -> leaf hashing -> digest layers -> cap.  At N > 1 the SAME commit is
+sharded over the ranks (strong scaling): columns for the iNTT, an NCCL all-gather of the coefficients, coset blocks /
+cap sub-trees for LDE + hashing, an all-gather of the cap entries.
+
+Prints ONE JSON line (rank 0).  `value` = ms per commit with inputs resident in HBM (device events, max over ranks);
+`e2e` = the same through the public API from pinned HOST buffers (H2D values, D2H coefficients + cap inside the timed
+region); `roofline` = the dominant kernel (leaf hashing) against measured HBM bandwidth, with `roofline_int` giving the
+figure that actually binds it (integer issue rate); `cpu_baseline` = the oracle port on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+SEED = 0x504C4F4E4B5932
+RATE_BITS, CAP_HEIGHT = 3, 4
+METRIC = "LDE+Merkle commit ms (2^20x135 cols, rate 3)"
+# dynamic thread-instructions of one Poseidon permutation in the shipped SASS (tools/sass_mix.py / ncu
+# smsp__inst_executed of hash_leaves_kernel divided by permutations; profiles/README.md)
+INSTR_PER_PERM = 24500
+INT_LANES_PER_CLK_PER_SM = 64  # measured IADD3 / IMAD issue rate on B200 (tools/int_peak.cu, profiles/int_peak_r01.md)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-log", type=int, default=20, help="log2 rows (development override; the judged run uses 20)")
+    ap.add_argument("--polys", type=int, default=135)
+    ap.add_argument("--cpu-sample-log", type=int, default=14, help="log2 rows of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index, self.samples, self._stop_evt, self.proc = gpu_index, [], threading.Event(), None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                if self._stop_evt.is_set():
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[1]))
+                mx.append(float(s[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        busy = [x for x in sm if x > 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port of the reference's CPU path, on all host threads
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_commit_ms(sample_log, polys, reps=1):
+    """Times PolynomialBatch::from_values of the oracle on a 2^sample_log x polys sample of the workload."""
+    import oracle
+    oracle.build()
+    rng = np.random.default_rng(SEED & 0xFFFFFFFF)
+    values = rng.integers(0, oracle.ORDER, size=(polys, 1 << sample_log), dtype=np.uint64)
+    best = None
+    for _ in range(reps):
+        t = time.perf_counter()
+        oracle.batch_from_values(values, RATE_BITS, CAP_HEIGHT, want_leaves=True, want_digests=True)
+        dt = (time.perf_counter() - t) * 1e3
+        best = dt if best is None else min(best, dt)
+    return best, oracle.get_threads()
+
+
+def cpu_baseline_obj(args, value_ms, cores, kind="port"):
+    scale = 1 << (args.n_log - args.cpu_sample_log)
+    return {"value": value_ms, "unit": "ms", "cores": cores, "kind": kind,
+            "sample": "oracle (C/OpenMP restatement of the reference CPU path) commit of 2^%d x %d, rate 3, cap 4, measured "
+                      "then scaled x%d to 2^%d rows (work is linear in rows up to the log factor of the NTT, which is <10%% of "
+                      "the time)" % (args.cpu_sample_log, args.polys, scale, args.n_log)}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    scale = 1 << (args.n_log - args.cpu_sample_log)
+    for _ in range(args.warmup):
+        cpu_commit_ms(args.cpu_sample_log, args.polys)
+    times, cores = [], 1
+    for _ in range(args.steps):
+        ms, cores = cpu_commit_ms(args.cpu_sample_log, args.polys)
+        times.append(ms * scale)
+    ms = sum(times) / len(times)
+    line = {"impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "PolynomialBatch::from_values 2^%d x %d Goldilocks, rate_bits 3, cap_height 4, Poseidon Merkle"
+                                   % (args.n_log, args.polys), "timing": "host wall clock of the CPU sample, scaled"},
+            "cpu_baseline": cpu_baseline_obj(args, ms, cores),
+            "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import plonky2_gpu_b200 as p2b
+    from plonky2_gpu_b200 import sharded
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    p2b.build()
+    ctx = p2b.Context(local_rank)
+    L = p2b.lib()
+    n_log, P = args.n_log, args.polys
+    n, N = 1 << n_log, 1 << (n_log + RATE_BITS)
+    c0, c1, cmax = sharded.column_shard(P, world, rank)
+
+    # ---- inputs resident in HBM: this rank's columns of the synthetic value matrix ----
+    vals = torch.empty((cmax, n), dtype=torch.int64, device="cuda")
+    work = torch.empty_like(vals)
+    torch.cuda.synchronize()
+    if c1 > c0:
+        p2b._check(L.p2b_fill_synthetic(ctx.handle, vals.data_ptr(), (c1 - c0) * n, SEED, c0 * n))
+    ctx.synchronize()
+    engine = sharded.GpuEngine(ctx)
+    comm = sharded.TorchComm(dist) if world > 1 else None
+
+    def barrier():
+        torch.cuda.synchronize()
+        ctx.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_device():
+        if world == 1:
+            b = p2b.PolynomialBatch.from_values(ctx, (_Ptr(vals.data_ptr()), P, n), RATE_BITS, CAP_HEIGHT)
+        else:
+            work.copy_(vals)  # the sharded path transforms its columns in place
+            b = sharded.sharded_commit_from_values(engine, comm, work, P, n_log, RATE_BITS, CAP_HEIGHT)
+        ctx.synchronize()
+        return b
+
+    class _Ptr:  # minimal DeviceBuffer stand-in for torch-owned memory
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+    # ---- warm-up ----
+    cap_check = None
+    for _ in range(max(args.warmup, 3)):
+        b = step_device()
+        cap_check = b.cap()
+        b.close()
+    barrier()
+
+    # ---- timed: device-resident ----
+    gpu_index = int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local_rank]) if os.environ.get("CUDA_VISIBLE_DEVICES") else local_rank
+    sampler = ClockSampler(gpu_index) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = ctx.launch_count
+    ctx.time_leaf_hash(True)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        b = step_device()
+        b.close()
+    dev_ms = ctx.timer_stop_ms()
+    barrier()
+    wall_ms = (time.perf_counter() - wall0) * 1e3
+    hash_ms, hash_launches = ctx.leaf_hash_time()
+    ctx.time_leaf_hash(False)
+    launches = ctx.launch_count - launches0
+    if sampler:
+        sampler.stop()
+    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = float(t[0]), float(t[1])
+    ms_per_step = dev_ms / args.steps
+
+    # ---- timed: end to end from pinned host buffers through the public API ----
+    host_vals = p2b.PinnedBuffer(max(cmax, 1) * n)
+    host_coef = p2b.PinnedBuffer(max(cmax, 1) * n)
+    host_vals.array[:] = vals.cpu().numpy().view(np.uint64).reshape(-1)
+    hv = host_vals.array.reshape(cmax, n)
+    hc = host_coef.array.reshape(cmax, n)
+    cap_host = np.empty((1 << CAP_HEIGHT, 4), dtype=np.uint64)
+
+    def step_e2e():
+        if world == 1:
+            b = p2b.PolynomialBatch.from_values(ctx, hv[:P], RATE_BITS, CAP_HEIGHT)   # H2D inside
+            b.cap(out=cap_host)                                                       # D2H result
+            b.polynomials(out=hc[:P])                                                 # D2H coefficients (the reference
+            b.close()                                                                 # keeps them host-side, oracle.rs:403-407)
+        else:
+            p2b._check(L.p2b_memcpy_h2d(ctx.handle, work.data_ptr(), host_vals.ptr, (c1 - c0) * n * 8))
+            b = sharded.sharded_commit_from_values(engine, comm, work, P, n_log, RATE_BITS, CAP_HEIGHT)
+            b.cap(out=cap_host)
+            # each rank returns the coefficient columns it transformed
+            ptrs = b.device_ptrs()
+            if c1 > c0:
+                p2b._check(L.p2b_memcpy_d2h(ctx.handle, host_coef.ptr, ptrs["coeffs"] + c0 * n * 8, (c1 - c0) * n * 8))
+            b.close()
+        ctx.synchronize()
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    w0 = time.perf_counter()
+    ctx.timer_start()
+    for _ in range(e2e_steps):
+        step_e2e()
+    e2e_dev = ctx.timer_stop_ms()
+    barrier()
+    e2e_wall = (time.perf_counter() - w0) * 1e3
+    t = torch.tensor([e2e_dev, e2e_wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t[1]) / e2e_steps  # host wall clock: the region contains host-side copies and API calls
+    h2d_bytes = P * n * 8
+    d2h_bytes = P * n * 8 + (1 << CAP_HEIGHT) * 32
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        clocks = sampler.summary() if sampler else {}
+        # roofline of the dominant kernel (leaf hashing): algorithmic bytes of one launch = the rows of one coset block
+        # read once + their digests written once (8*leaf_len per leaf in, 32 B per leaf out)
+        leaves_per_launch = n * (1 << RATE_BITS) // world // max(1, (1 << RATE_BITS) // world)  # = n
+        alg_bytes = leaves_per_launch * (P * 8 + 32)
+        avg_hash_ms = hash_ms / max(hash_launches, 1)
+        achieved_gbs = alg_bytes / (avg_hash_ms * 1e-3) / 1e9 if avg_hash_ms > 0 else 0.0
+        perms_per_launch = leaves_per_launch * (-(-P // 8))
+        sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+        int_peak = INT_LANES_PER_CLK_PER_SM * 148 * sm_mhz * 1e6          # thread-instructions / s
+        int_ach = perms_per_launch * INSTR_PER_PERM / (avg_hash_ms * 1e-3) if avg_hash_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "PolynomialBatch::from_values 2^%d x %d Goldilocks, rate_bits 3, cap_height 4, Poseidon Merkle "
+                                   "(BASELINE.json configs[1])" % (n_log, P),
+                       "sharding": "columns for iNTT, coset blocks / cap sub-trees for LDE+Merkle" if world > 1 else "single GPU",
+                       "l2": "inputs_exceed_l2 (values %.2f GB, LDE %.2f GB per step vs 126 MB L2)" % (P * n * 8 / 1e9, P * N * 8 / 1e9),
+                       "timing": "CUDA events on the library stream around all steps, max over ranks; wall %.1f ms/step" % (wall_ms / args.steps),
+                       "cap_word0": "%016x" % int(cap_check[0][0])},
+            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                    "steps": e2e_steps, "note": "pinned host values -> p2b_commit_from_values -> D2H coefficients + cap; host wall clock, max over ranks"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "merkle::hash_leaves_kernel", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind + " (burst copy bandwidth)",
+                         "launches_timed": hash_launches, "avg_launch_ms": avg_hash_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "share_of_step": hash_ms / max(dev_ms, 1e-9)},
+            "roofline_int": {"bound": "integer issue (64 INT32 lanes/clk/SM measured)", "achieved": int_ach / 1e12, "peak": int_peak / 1e12,
+                             "unit": "T thread-instr/s", "frac": int_ach / int_peak if int_peak else None,
+                             "perm_per_s": perms_per_launch / (avg_hash_ms * 1e-3) if avg_hash_ms > 0 else None,
+                             "instr_per_permutation": INSTR_PER_PERM, "sm_mhz": sm_mhz},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            ms, cores = cpu_commit_ms(args.cpu_sample_log, P, reps=2)
+            line["cpu_baseline"] = cpu_baseline_obj(args, ms * (1 << (n_log - args.cpu_sample_log)), cores)
+        print(json.dumps(line), flush=True)
+    host_vals.free()
+    host_coef.free()
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and not (world == 1 and args.impl == "reference"):
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun: python -m torch.distributed.run --nnodes=1 --nproc-per-node %d "
+                             "--master-addr 127.0.0.1 --master-port 29501 bench.py --gpus %d ..." % (args.gpus, args.gpus, args.gpus))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -63,6 +63,10 @@ void* p2b_ctx_stream(p2b_ctx* ctx);
 int p2b_ctx_synchronize(p2b_ctx* ctx);
 /* Kernels launched by this context since creation (for bench.py's gpu_launches). */
 uint64_t p2b_ctx_launch_count(const p2b_ctx* ctx);
+/* Live timing of the dominant kernel (leaf hashing) with CUDA events on the stream it is launched on: enable, run
+ * commits, then read the summed duration and the number of launches timed (bench.py's roofline figure). */
+int p2b_ctx_time_leaf_hash(p2b_ctx* ctx, int enable);
+int p2b_ctx_leaf_hash_time(p2b_ctx* ctx, double* total_ms, uint64_t* launches);
 
 /* ---------------------------------------------------------------------------------------------------
  * PolynomialBatch::from_values / from_coeffs
@@ -113,6 +117,25 @@ int p2b_batch_prove(const p2b_batch* b, const uint64_t* leaf_indices, uint64_t c
 /* Rows + proofs for FRI query rounds in one gather (fri/prover.rs:187-216 reads them row by row). */
 int p2b_batch_open_rows(const p2b_batch* b, const uint64_t* leaf_indices, uint64_t count,
                         uint64_t* rows_out /* [count][leaf_len] */, uint64_t* siblings_out /* or NULL */);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Sharded commit (multi-GPU).  The LDE domain splits into 2^rate_bits cosets; in leaf order
+ * coset block b is the contiguous leaf range [b*n, (b+1)*n).  A rank commits a contiguous range of blocks from the
+ * full coefficient matrix (device, [P][n]): it holds only its own leaf rows, writes its digests into a buffer with
+ * the whole tree's layout, and computes digest layers for as long as whole nodes lie inside its leaf range
+ * (`top_layer`).  If top_layer reaches the cap (always when 2^cap_height >= number of ranks) the ranks only
+ * exchange cap entries; otherwise they exchange their top-layer nodes with export/import and call
+ * p2b_batch_finish_layers.  The exchange itself (NCCL all-gather) is done by the caller on the device buffers.
+ * ------------------------------------------------------------------------------------------------- */
+int p2b_commit_blocks(p2b_ctx* ctx, const uint64_t* d_coeffs, uint32_t n_log, uint64_t P, uint32_t rate_bits,
+                      uint32_t cap_height, const uint64_t* d_salt /* device [4][N] or NULL */, uint64_t block_first,
+                      uint64_t block_count, p2b_batch** out);
+int p2b_batch_shard_info(const p2b_batch* b, uint64_t* first_leaf, uint64_t* local_leaves, uint32_t* top_layer,
+                         uint64_t* top_node_first, uint64_t* top_node_count);
+int p2b_batch_export_nodes(const p2b_batch* b, uint32_t layer, uint64_t node_first, uint64_t count,
+                           uint64_t* d_out /* device [count][4] */);
+int p2b_batch_import_nodes(p2b_batch* b, uint32_t layer, uint64_t node_first, uint64_t count, const uint64_t* d_in);
+int p2b_batch_finish_layers(p2b_batch* b, uint32_t from_layer);
 
 /* ---------------------------------------------------------------------------------------------------
  * Building blocks (device pointers unless stated).  Each mirrors one reference function.

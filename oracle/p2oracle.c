@@ -294,10 +294,14 @@ static inline uint64_t sbox(uint64_t x) {
 }
 /* mds_row_shf + mds_layer, poseidon.rs:172-194, 236-260 */
 static inline void mds_layer(uint64_t* s) {
-  uint64_t out[W];
+  uint64_t out[W], d[2 * W];
+  memcpy(d, s, W * sizeof(uint64_t));
+  memcpy(d + W, s, W * sizeof(uint64_t)); /* doubled copy: s[(i + r) % W] == d[i + r] */
+#pragma GCC unroll 12
   for (int r = 0; r < W; r++) {
     u128 acc = 0;
-    for (int i = 0; i < W; i++) acc += (u128)s[(i + r) % W] * (u128)P2_MDS_CIRC[i];
+#pragma GCC unroll 12
+    for (int i = 0; i < W; i++) acc += (u128)d[i + r] * (u128)P2_MDS_CIRC[i];
     acc += (u128)s[r] * (u128)P2_MDS_DIAG[r];
     out[r] = f_reduce96((uint64_t)acc, (uint32_t)(acc >> 64));
   }
@@ -319,9 +323,20 @@ static inline void partial_rounds(uint64_t* s, int* round_ctr) {
     uint64_t res[W];
     memset(res, 0, sizeof(res));
     res[0] = s[0];
-    for (int r = 1; r < W; r++)
-      for (int c = 1; c < W; c++)
-        res[c] = f_add(res[c], f_mul(s[r], P2_PARTIAL_INIT_MATRIX[(r - 1) * 11 + (c - 1)]));
+    /* same sums as the reference's loop nest (:319-333), accumulated per output column in a u160 so that the
+     * CPU baseline is not penalised by 121 separate reductions (field addition is exact, the result is equal) */
+    for (int c = 1; c < W; c++) {
+      u128 lo = 0;
+      uint32_t hi = 0;
+#pragma GCC unroll 11
+      for (int r = 1; r < W; r++) {
+        u128 t = (u128)s[r] * (u128)P2_PARTIAL_INIT_MATRIX[(r - 1) * 11 + (c - 1)];
+        u128 nl = lo + t;
+        hi += nl < lo;
+        lo = nl;
+      }
+      res[c] = f_reduce160(lo, hi);
+    }
     memcpy(s, res, sizeof(res));
   }
   for (int r = 0; r < 22; r++) {
@@ -330,6 +345,7 @@ static inline void partial_rounds(uint64_t* s, int* round_ctr) {
     /* mds_partial_layer_fast: d = M00*s0 + sum w_hat[i-1]*s[i] in a u160 accumulator */
     u128 lo = 0;
     uint32_t hi = 0;
+#pragma GCC unroll 11
     for (int i = 1; i < W; i++) {
       u128 t = (u128)s[i] * (u128)P2_PARTIAL_W_HATS[r * 11 + i - 1];
       u128 nl = lo + t;
@@ -345,6 +361,7 @@ static inline void partial_rounds(uint64_t* s, int* round_ctr) {
     uint64_t d = f_reduce160(lo, hi);
     uint64_t s0 = s[0];
     s[0] = d;
+#pragma GCC unroll 11
     for (int i = 1; i < W; i++) /* multiply_accumulate, goldilocks_field.rs:123-127 */
       s[i] = f_reduce128((u128)s[i] + (u128)s0 * (u128)P2_PARTIAL_VS[r * 11 + i - 1]);
   }

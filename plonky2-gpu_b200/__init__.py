@@ -71,6 +71,8 @@ def lib():
         "p2b_ctx_stream": (vp, [vp]),
         "p2b_ctx_synchronize": (i, [vp]),
         "p2b_ctx_launch_count": (u64, [vp]),
+        "p2b_ctx_time_leaf_hash": (i, [vp, i]),
+        "p2b_ctx_leaf_hash_time": (i, [vp, C.POINTER(C.c_double), C.POINTER(u64)]),
         "p2b_commit_from_values": (i, [vp, vp, i, u32, u64, u32, u32, vp, i, C.POINTER(vp)]),
         "p2b_commit_from_coeffs": (i, [vp, vp, i, u32, u64, u32, u32, vp, i, C.POINTER(vp)]),
         "p2b_batch_destroy": (None, [vp]),
@@ -83,6 +85,11 @@ def lib():
         "p2b_batch_get_lde_values": (i, [vp, u64, u64, vp]),
         "p2b_batch_prove": (i, [vp, vp, u64, vp]),
         "p2b_batch_open_rows": (i, [vp, vp, u64, vp, vp]),
+        "p2b_commit_blocks": (i, [vp, vp, u32, u64, u32, u32, vp, u64, u64, C.POINTER(vp)]),
+        "p2b_batch_shard_info": (i, [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u32), C.POINTER(u64), C.POINTER(u64)]),
+        "p2b_batch_export_nodes": (i, [vp, u32, u64, u64, vp]),
+        "p2b_batch_import_nodes": (i, [vp, u32, u64, u64, vp]),
+        "p2b_batch_finish_layers": (i, [vp, u32]),
         "p2b_ifft_batch": (i, [vp, vp, vp, u32, u64]),
         "p2b_lde_leaves": (i, [vp, vp, u32, u64, u32, vp, u64, u64]),
         "p2b_merkle_tree": (i, [vp, vp, u64, u64, u64, u64, u32, vp, vp]),
@@ -198,6 +205,14 @@ class Context:
     @property
     def launch_count(self):
         return int(lib().p2b_ctx_launch_count(self.handle))
+
+    def time_leaf_hash(self, enable=True):
+        _check(lib().p2b_ctx_time_leaf_hash(self.handle, 1 if enable else 0))
+
+    def leaf_hash_time(self):
+        ms, n = C.c_double(), C.c_uint64()
+        _check(lib().p2b_ctx_leaf_hash_time(self.handle, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
 
     def timer_start(self):
         _check(lib().p2b_timer_start(self.handle))
@@ -338,13 +353,18 @@ class PolynomialBatch:
         except Exception:
             pass
 
+    def shard_info(self):
+        a, b, t, f, n = C.c_uint64(), C.c_uint64(), C.c_uint32(), C.c_uint64(), C.c_uint64()
+        _check(lib().p2b_batch_shard_info(self.handle, C.byref(a), C.byref(b), C.byref(t), C.byref(f), C.byref(n)))
+        return {"first_leaf": a.value, "local_leaves": b.value, "top_layer": t.value, "top_node_first": f.value, "top_node_count": n.value}
+
     def device_ptrs(self):
         a, b, c, d = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
         _check(lib().p2b_batch_device_ptrs(self.handle, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return {"coeffs": a.value, "leaves": b.value, "digests": c.value, "cap": d.value}
 
-    def polynomials(self):
-        out = np.empty((self.num_polys, 1 << self.degree_log), dtype=np.uint64)
+    def polynomials(self, out=None):
+        out = np.empty((self.num_polys, 1 << self.degree_log), dtype=np.uint64) if out is None else out
         _check(lib().p2b_batch_get_coeffs(self.handle, out.ctypes.data))
         return out
 
@@ -359,8 +379,11 @@ class PolynomialBatch:
             _check(lib().p2b_batch_get_digests(self.handle, out.ctypes.data))
         return out
 
-    def leaves(self, first=0, count=None):
-        count = self.num_leaves - first if count is None else count
+    def leaves(self, first=None, count=None):
+        if first is None or count is None:
+            si = self.shard_info()
+            first = si["first_leaf"] if first is None else first
+            count = si["first_leaf"] + si["local_leaves"] - first if count is None else count
         out = np.empty((count, self.leaf_len), dtype=np.uint64)
         _check(lib().p2b_batch_get_leaves(self.handle, first, count, out.ctypes.data))
         return out

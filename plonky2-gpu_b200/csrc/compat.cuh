@@ -91,7 +91,7 @@ static int compat_from_coeffs(p2b_ctx* c, RefStreams* rs, u64* base, int poly_nu
   // intermediates live in the work area; coset blocks are produced in descending order so that block 0,
   // whose rows overwrite the coefficients, is written last and only after stream2's copy has finished.
   return lde_and_merkle(c, coeffs, (u32)log_len, P, (u32)rate_bits, (u32)cap_height, nullptr, work, base, P, digests, cap,
-                        true, rs ? rs->stream2 : nullptr);
+                        true, rs ? rs->stream2 : nullptr, 0, (u64)1 << rate_bits, nullptr);
 }
 
 // merkle_tree_from_coeffs (cuda/plonky2_gpu.cu:435-606; oracle.rs:409-422, 599-627)

@@ -106,6 +106,10 @@ struct p2b_ctx {
   u64* scratch = nullptr;
   u64 scratch_elems = 0;
   u64 launches = 0;
+  // optional per-kernel timing of the dominant kernel (leaf hashing): event pairs on the launching stream
+  bool time_hash = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> hash_events;
+  size_t hash_events_used = 0;
   int sm_count = 148;
   size_t smem_optin = 0;
 };
@@ -221,6 +225,10 @@ extern "C" void p2b_ctx_destroy(p2b_ctx* c) {
   cudaFree(c->scratch);
   for (cudaEvent_t e : {c->ev_a, c->ev_b, c->ev_t0, c->ev_t1})
     if (e) cudaEventDestroy(e);
+  for (auto& pr : c->hash_events) {
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
   if (c->owns_streams) {
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->stream2) cudaStreamDestroy(c->stream2);
@@ -236,6 +244,26 @@ extern "C" int p2b_ctx_synchronize(p2b_ctx* c) {
   return P2B_OK;
 }
 extern "C" uint64_t p2b_ctx_launch_count(const p2b_ctx* c) { return c ? c->launches : 0; }
+extern "C" int p2b_ctx_time_leaf_hash(p2b_ctx* c, int enable) {
+  if (!c) return fail(P2B_ERR_INVALID, "ctx is NULL");
+  c->time_hash = enable != 0;
+  c->hash_events_used = 0;
+  return P2B_OK;
+}
+extern "C" int p2b_ctx_leaf_hash_time(p2b_ctx* c, double* total_ms, uint64_t* launches) {
+  if (!c || !total_ms || !launches) return fail(P2B_ERR_INVALID, "NULL argument");
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream2));
+  double t = 0;
+  for (size_t i = 0; i < c->hash_events_used; i++) {
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, c->hash_events[i].first, c->hash_events[i].second));
+    t += ms;
+  }
+  *total_ms = t;
+  *launches = c->hash_events_used;
+  return P2B_OK;
+}
 
 // ======================================================================================================
 // pass planner
@@ -345,7 +373,7 @@ static ntt::LevelScale lde_scale(u32 k) {
 
 // One coset block b of the LDE: coeffs [P][n] -> rows [b*n, (b+1)*n) of leaves (row-major).
 static int run_lde_block(p2b_ctx* c, cudaStream_t st, const u64* coeffs, u64 coeffs_cs, u64* tmp, u32 k, u64 P,
-                         u64 b, const ntt::LevelScale& sc, u64* leaves, u64 row_stride, u64 col0) {
+                         u64 b, const ntt::LevelScale& sc, u64* leaves, u64 row_stride, u64 col0, u64 row0) {
   Plan pl = make_plan(k);
   const u64 n = (u64)1 << k;
   ntt::PassArgs a{};
@@ -376,7 +404,7 @@ static int run_lde_block(p2b_ctx* c, cudaStream_t st, const u64* coeffs, u64 coe
   size_t smem = (((size_t)(FINAL_C + 1) << a.L) + ((size_t)1 << a.L)) * 8;
   P2B_TRY(opt_in_smem(ntt::ntt_final_pass_kernel<FINAL_C, ntt::MODE_ROWS>, smem));
   dim3 grid((unsigned)((u64)1 << a.s0), (unsigned)((P + FINAL_C - 1) / FINAL_C));
-  ntt::ntt_final_pass_kernel<FINAL_C, ntt::MODE_ROWS><<<grid, 512, smem, st>>>(a, sc, b * n, row_stride, col0);
+  ntt::ntt_final_pass_kernel<FINAL_C, ntt::MODE_ROWS><<<grid, 512, smem, st>>>(a, sc, row0, row_stride, col0);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   return P2B_OK;
@@ -390,31 +418,53 @@ static int launch_hash_leaves(p2b_ctx* c, cudaStream_t st, const u64* leaves, u6
                               u64* cap) {
   if (count == 0) return P2B_OK;
   unsigned blocks = (unsigned)((count + P2B_HASH_BLOCK - 1) / P2B_HASH_BLOCK);
-  merkle::hash_leaves_kernel<<<blocks, P2B_HASH_BLOCK, 0, st>>>(leaves + first_leaf * row_stride, row_stride, col_stride, leaf_len,
-                                                     count, first_leaf, shape, digests, cap);
+  // `leaves` points at the first leaf of this launch; first_leaf is its global index in the tree
+  std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
+  if (c->time_hash) {
+    if (c->hash_events_used == c->hash_events.size()) {
+      cudaEvent_t a, b;
+      CUDA_TRY(cudaEventCreate(&a));
+      CUDA_TRY(cudaEventCreate(&b));
+      c->hash_events.emplace_back(a, b);
+    }
+    ev = &c->hash_events[c->hash_events_used++];
+    CUDA_TRY(cudaEventRecord(ev->first, st));
+  }
+  merkle::hash_leaves_kernel<<<blocks, P2B_HASH_BLOCK, 0, st>>>(leaves, row_stride, col_stride, leaf_len, count, first_leaf, shape,
+                                                                digests, cap);
+  if (ev) CUDA_TRY(cudaEventRecord(ev->second, st));
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   return P2B_OK;
 }
-static int launch_layers(p2b_ctx* c, cudaStream_t st, const merkle::TreeShape& shape, u64* digests, u64* cap) {
-  for (u32 l = 1; l <= shape.sub_log; l++) {
-    u64 count = shape.num_leaves >> l;
+// Digest layers above the leaves [leaf0, leaf1) for as long as whole nodes fit that range, starting above
+// `from_layer`.  Returns the last layer computed (== shape.sub_log when the range reaches the cap).
+static int launch_layers(p2b_ctx* c, cudaStream_t st, const merkle::TreeShape& shape, u64* digests, u64* cap,
+                         u64 leaf0, u64 leaf1, u32 from_layer, u32* top_layer) {
+  u32 l = from_layer;
+  while (l < shape.sub_log) {
+    u64 span = (u64)1 << (l + 1);
+    if ((leaf0 % span) || (leaf1 % span) || leaf1 <= leaf0) break;
+    l++;
+    u64 node0 = leaf0 >> l, count = (leaf1 - leaf0) >> l;
     unsigned blocks = (unsigned)((count + P2B_HASH_BLOCK - 1) / P2B_HASH_BLOCK);
-    merkle::merkle_layer_kernel<<<blocks, P2B_HASH_BLOCK, 0, st>>>(shape, l, 0, count, digests, cap);
+    merkle::merkle_layer_kernel<<<blocks, P2B_HASH_BLOCK, 0, st>>>(shape, l, node0, count, digests, cap);
     c->launches++;
   }
   CUDA_TRY(cudaGetLastError());
+  if (top_layer) *top_layer = l;
   return P2B_OK;
 }
 
 // leaf row L, column P + c  <-  salt[c][reverse_bits(L)]   (oracle.rs:998-1002 then :942-952)
-__global__ void scatter_salt_kernel(const u64* __restrict__ salt, u64 N, u32 log_N, u64* __restrict__ leaves,
-                                    u64 row_stride, u64 col0) {
-  u64 L = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (L >= N) return;
+__global__ void scatter_salt_kernel(const u64* __restrict__ salt, u64 N, u32 log_N, u64 leaf0, u64 count,
+                                    u64* __restrict__ leaves, u64 row_stride, u64 col0) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  u64 L = leaf0 + i;
   u64 src = log_N ? (__brevll(L) >> (64 - log_N)) : 0;
 #pragma unroll
-  for (int cidx = 0; cidx < P2B_SALT_SIZE; cidx++) leaves[L * row_stride + col0 + cidx] = gl::canon(salt[(u64)cidx * N + src]);
+  for (int cidx = 0; cidx < P2B_SALT_SIZE; cidx++) leaves[i * row_stride + col0 + cidx] = gl::canon(salt[(u64)cidx * N + src]);
 }
 
 // ======================================================================================================
@@ -423,6 +473,8 @@ __global__ void scatter_salt_kernel(const u64* __restrict__ salt, u64 N, u32 log
 struct p2b_batch {
   p2b_ctx* ctx = nullptr;
   p2b_batch_info info{};
+  u64 first_leaf = 0, local_leaves = 0;  // rows held by this (possibly sharded) batch: [first_leaf, first_leaf + local_leaves)
+  u32 top_layer = 0;                     // highest digest layer computed from local leaves
   u64* coeffs = nullptr;
   u64* leaves = nullptr;
   u64* digests = nullptr;
@@ -447,37 +499,42 @@ extern "C" void p2b_batch_destroy(p2b_batch* b) { batch_free(b); }
 //   (needed when leaves_d aliases coeffs_d: block 0's rows overwrite the coefficients last).
 static int lde_and_merkle(p2b_ctx* c, const u64* coeffs_d, u32 k, u64 P, u32 rate_bits, u32 cap_height,
                           const u64* salt_d, u64* tmp, u64* leaves_d, u64 leaf_len, u64* digests_d, u64* cap_d,
-                          bool descending, cudaStream_t wait_before_block0) {
-  const u64 n = (u64)1 << k, R = (u64)1 << rate_bits, N = n << rate_bits;
+                          bool descending, cudaStream_t wait_before_block0, u64 block_first, u64 block_count,
+                          u32* top_layer) {
+  // leaves_d row 0 is global leaf block_first * n (a shard holds only its own coset blocks' rows)
+  const u64 n = (u64)1 << k, N = n << rate_bits;
   const u32 log_N = k + rate_bits;
   if (cap_height > log_N)
     return fail(P2B_ERR_INVALID, "cap_height=%u should be at most log2(leaves.len())=%u", cap_height, log_N);
   P2B_TRY(ensure_twiddles(c, log_N > 0 ? log_N - 1 : 0));
   merkle::TreeShape shape = merkle::make_shape(log_N, cap_height);
   ntt::LevelScale sc = lde_scale(k);
+  const u64 leaf0 = block_first * n, nleaves = block_count * n;
   if (salt_d) {
-    scatter_salt_kernel<<<(unsigned)((N + 255) / 256), 256, 0, c->stream>>>(salt_d, N, log_N, leaves_d, leaf_len, P);
+    scatter_salt_kernel<<<(unsigned)((nleaves + 255) / 256), 256, 0, c->stream>>>(salt_d, N, log_N, leaf0, nleaves, leaves_d,
+                                                                                 leaf_len, P);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
   }
-  // stream2 must not start hashing before earlier work on `stream` (salt scatter, previous users) is ordered
-  for (u64 i = 0; i < R; i++) {
-    u64 b = descending ? R - 1 - i : i;
+  for (u64 i = 0; i < block_count; i++) {
+    u64 b = block_first + (descending ? block_count - 1 - i : i);
     if (b == 0 && wait_before_block0) CUDA_TRY(cudaStreamSynchronize(wait_before_block0));
-    P2B_TRY(run_lde_block(c, c->stream, coeffs_d, n, tmp, k, P, b, sc, leaves_d, leaf_len, 0));
+    P2B_TRY(run_lde_block(c, c->stream, coeffs_d, n, tmp, k, P, b, sc, leaves_d, leaf_len, 0, (b - block_first) * n));
     // hash this block's rows on stream2 while the next block's NTT runs on stream
     CUDA_TRY(cudaEventRecord(c->ev_a, c->stream));
     CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->ev_a, 0));
-    P2B_TRY(launch_hash_leaves(c, c->stream2, leaves_d, leaf_len, 1, (u32)leaf_len, b * n, n, shape, digests_d, cap_d));
+    P2B_TRY(launch_hash_leaves(c, c->stream2, leaves_d + (b - block_first) * n * leaf_len, leaf_len, 1, (u32)leaf_len, b * n, n,
+                               shape, digests_d, cap_d));
   }
   CUDA_TRY(cudaEventRecord(c->ev_b, c->stream2));
   CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
-  P2B_TRY(launch_layers(c, c->stream, shape, digests_d, cap_d));
+  P2B_TRY(launch_layers(c, c->stream, shape, digests_d, cap_d, leaf0, leaf0 + nleaves, 0, top_layer));
   return P2B_OK;
 }
 
 static int commit_impl(p2b_ctx* c, const u64* input, int on_host, bool is_values, u32 k, u64 P, u32 rate_bits,
-                       u32 cap_height, const u64* salt, int salt_on_host, p2b_batch** out) {
+                       u32 cap_height, const u64* salt, int salt_on_host, p2b_batch** out, u64 block_first = 0,
+                       u64 block_count = ~(u64)0) {
   if (!c || !out) return fail(P2B_ERR_INVALID, "NULL argument");
   *out = nullptr;
   if (!input || P == 0) return fail(P2B_ERR_INVALID, "empty batch (no polynomials)");
@@ -490,19 +547,26 @@ static int commit_impl(p2b_ctx* c, const u64* input, int on_host, bool is_values
   CUDA_TRY(cudaSetDevice(c->device));
   const u64 salt_size = salt ? P2B_SALT_SIZE : 0, leaf_len = P + salt_size;
   const u64 ncap = (u64)1 << cap_height, ndig = 2 * (N - ncap);
+  const u64 R = (u64)1 << rate_bits;
+  if (block_count == ~(u64)0) block_count = R - block_first;
+  if (block_first >= R || block_count == 0 || block_first + block_count > R)
+    return fail(P2B_ERR_INVALID, "coset block range [%llu, +%llu) outside 2^rate_bits = %llu", (unsigned long long)block_first,
+                (unsigned long long)block_count, (unsigned long long)R);
 
   p2b_batch* b = new (std::nothrow) p2b_batch();
   if (!b) return fail(P2B_ERR_OOM, "host allocation failed");
   b->ctx = c;
   b->info = p2b_batch_info{k, rate_bits, cap_height, (u32)salt_size, P, N, leaf_len, ndig};
   b->shape = merkle::make_shape(log_N, cap_height);
+  b->first_leaf = block_first * n;
+  b->local_leaves = block_count * n;
   cudaStream_t st = c->stream;
   u64* staged = nullptr;  // device copy of host input
   u64* salt_d = nullptr;
   int rc = P2B_OK;
   auto body = [&]() -> int {
     CUDA_TRY(cudaMallocAsync(&b->coeffs, P * n * sizeof(u64), st));
-    CUDA_TRY(cudaMallocAsync(&b->leaves, N * leaf_len * sizeof(u64), st));
+    CUDA_TRY(cudaMallocAsync(&b->leaves, b->local_leaves * leaf_len * sizeof(u64), st));
     CUDA_TRY(cudaMallocAsync(&b->digests, (ndig ? ndig : 1) * 4 * sizeof(u64), st));
     CUDA_TRY(cudaMallocAsync(&b->cap, ncap * 4 * sizeof(u64), st));
     P2B_TRY(ensure_scratch(c, P * n));
@@ -526,7 +590,7 @@ static int commit_impl(p2b_ctx* c, const u64* input, int on_host, bool is_values
       CUDA_TRY(cudaMemcpyAsync(b->coeffs, input, P * n * sizeof(u64), cudaMemcpyDeviceToDevice, st));
     }
     P2B_TRY(lde_and_merkle(c, b->coeffs, k, P, rate_bits, cap_height, salt_d, c->scratch, b->leaves, leaf_len,
-                           b->digests, b->cap, false, nullptr));
+                           b->digests, b->cap, false, nullptr, block_first, block_count, &b->top_layer));
     return P2B_OK;
   };
   rc = body();
@@ -549,6 +613,61 @@ extern "C" int p2b_commit_from_coeffs(p2b_ctx* ctx, const uint64_t* coeffs, int 
                                       uint64_t P, uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt,
                                       int salt_on_host, p2b_batch** out) {
   return commit_impl(ctx, coeffs, coeffs_on_host, false, n_log, P, rate_bits, cap_height, salt, salt_on_host, out);
+}
+
+// ---- sharded commit (multi-GPU): one rank = a contiguous range of coset blocks ------------------------------
+extern "C" int p2b_commit_blocks(p2b_ctx* ctx, const uint64_t* d_coeffs, uint32_t n_log, uint64_t P, uint32_t rate_bits,
+                                 uint32_t cap_height, const uint64_t* d_salt, uint64_t block_first, uint64_t block_count,
+                                 p2b_batch** out) {
+  return commit_impl(ctx, d_coeffs, 0, false, n_log, P, rate_bits, cap_height, d_salt, 0, out, block_first, block_count);
+}
+extern "C" int p2b_batch_shard_info(const p2b_batch* b, uint64_t* first_leaf, uint64_t* local_leaves, uint32_t* top_layer,
+                                    uint64_t* top_node_first, uint64_t* top_node_count) {
+  if (!b) return fail(P2B_ERR_INVALID, "NULL batch");
+  if (first_leaf) *first_leaf = b->first_leaf;
+  if (local_leaves) *local_leaves = b->local_leaves;
+  if (top_layer) *top_layer = b->top_layer;
+  if (top_node_first) *top_node_first = b->first_leaf >> b->top_layer;
+  if (top_node_count) *top_node_count = b->local_leaves >> b->top_layer;
+  return P2B_OK;
+}
+// nodes [node_first, +count) of digest layer `layer` <-> contiguous device buffer [count][4]
+__global__ void move_nodes_kernel(merkle::TreeShape shape, u32 layer, u64 node_first, u64 count, u64* digests, u64* cap,
+                                  u64* buf, int import) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count * 4) return;
+  u64* slot = merkle::node_slot(shape, digests, cap, layer, node_first + (i >> 2)) + (i & 3);
+  if (import) *slot = buf[i];
+  else buf[i] = *slot;
+}
+static int move_nodes(const p2b_batch* b, u32 layer, u64 node_first, u64 count, u64* d_buf, int import) {
+  if (!b || !d_buf) return fail(P2B_ERR_INVALID, "NULL argument");
+  if (layer > b->shape.sub_log || node_first + count > (b->info.num_leaves >> layer)) return fail(P2B_ERR_INVALID, "node range out of bounds");
+  if (count == 0) return P2B_OK;
+  p2b_ctx* c = b->ctx;
+  CUDA_TRY(cudaSetDevice(c->device));
+  move_nodes_kernel<<<(unsigned)((count * 4 + 255) / 256), 256, 0, c->stream>>>(b->shape, layer, node_first, count, b->digests, b->cap,
+                                                                          d_buf, import);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return P2B_OK;
+}
+extern "C" int p2b_batch_export_nodes(const p2b_batch* b, uint32_t layer, uint64_t node_first, uint64_t count, uint64_t* d_out) {
+  return move_nodes(b, layer, node_first, count, d_out, 0);
+}
+extern "C" int p2b_batch_import_nodes(p2b_batch* b, uint32_t layer, uint64_t node_first, uint64_t count, const uint64_t* d_in) {
+  return move_nodes(b, layer, node_first, count, const_cast<u64*>(d_in), 1);
+}
+// after every shard's top-layer nodes have been imported: the remaining layers up to the cap (whole tree)
+extern "C" int p2b_batch_finish_layers(p2b_batch* b, uint32_t from_layer) {
+  if (!b) return fail(P2B_ERR_INVALID, "NULL batch");
+  if (from_layer > b->shape.sub_log) return fail(P2B_ERR_INVALID, "layer out of range");
+  p2b_ctx* c = b->ctx;
+  CUDA_TRY(cudaSetDevice(c->device));
+  u32 top = 0;
+  P2B_TRY(launch_layers(c, c->stream, b->shape, b->digests, b->cap, 0, b->info.num_leaves, from_layer, &top));
+  b->top_layer = top;
+  return P2B_OK;
 }
 
 extern "C" int p2b_batch_get_info(const p2b_batch* b, p2b_batch_info* out) {
@@ -588,8 +707,10 @@ extern "C" int p2b_batch_get_digests(const p2b_batch* b, uint64_t* out) {
 }
 extern "C" int p2b_batch_get_leaves(const p2b_batch* b, uint64_t first_leaf, uint64_t count, uint64_t* out) {
   if (!b) return fail(P2B_ERR_INVALID, "NULL batch");
-  if (first_leaf + count > b->info.num_leaves) return fail(P2B_ERR_INVALID, "leaf range out of bounds");
-  return d2h(b, out, b->leaves + first_leaf * b->info.leaf_len, count * b->info.leaf_len * sizeof(u64));
+  if (first_leaf < b->first_leaf || first_leaf + count > b->first_leaf + b->local_leaves)
+    return fail(P2B_ERR_INVALID, "leaf range out of bounds (this batch holds leaves [%llu, %llu))", (unsigned long long)b->first_leaf,
+                (unsigned long long)(b->first_leaf + b->local_leaves));
+  return d2h(b, out, b->leaves + (first_leaf - b->first_leaf) * b->info.leaf_len, count * b->info.leaf_len * sizeof(u64));
 }
 extern "C" int p2b_batch_get_lde_values(const p2b_batch* b, uint64_t index, uint64_t step, uint64_t* out) {
   if (!b) return fail(P2B_ERR_INVALID, "NULL batch");
@@ -598,7 +719,9 @@ extern "C" int p2b_batch_get_lde_values(const p2b_batch* b, uint64_t index, uint
   if (i >= b->info.num_leaves) return fail(P2B_ERR_INVALID, "index*step out of the LDE domain");
   u64 row = 0;
   for (u32 t = 0; t < bits; t++) row |= ((i >> t) & 1) << (bits - 1 - t);  // reverse_bits, util/mod.rs:55-63
-  return d2h(b, out, b->leaves + row * b->info.leaf_len, b->info.num_polys * sizeof(u64));
+  if (row < b->first_leaf || row >= b->first_leaf + b->local_leaves)
+    return fail(P2B_ERR_INVALID, "row %llu is held by another shard", (unsigned long long)row);
+  return d2h(b, out, b->leaves + (row - b->first_leaf) * b->info.leaf_len, b->info.num_polys * sizeof(u64));
 }
 
 // gather rows and/or Merkle paths for a list of leaf indices
@@ -631,7 +754,9 @@ static int open_impl(const p2b_batch* b, const u64* leaf_indices, u64 count, u64
   if (!b || !leaf_indices) return fail(P2B_ERR_INVALID, "NULL argument");
   if (count == 0) return P2B_OK;
   for (u64 i = 0; i < count; i++)
-    if (leaf_indices[i] >= b->info.num_leaves) return fail(P2B_ERR_INVALID, "leaf index %llu out of range", (unsigned long long)leaf_indices[i]);
+    if (leaf_indices[i] < b->first_leaf || leaf_indices[i] >= b->first_leaf + b->local_leaves)
+      return fail(P2B_ERR_INVALID, "leaf index %llu out of range (this batch holds leaves [%llu, %llu))", (unsigned long long)leaf_indices[i],
+                  (unsigned long long)b->first_leaf, (unsigned long long)(b->first_leaf + b->local_leaves));
   p2b_ctx* c = b->ctx;
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
@@ -642,7 +767,7 @@ static int open_impl(const p2b_batch* b, const u64* leaf_indices, u64 count, u64
     CUDA_TRY(cudaMemcpyAsync(d_idx, leaf_indices, count * sizeof(u64), cudaMemcpyHostToDevice, st));
     if (rows_out) CUDA_TRY(cudaMallocAsync(&d_rows, count * ll * sizeof(u64), st));
     if (sibs_out && layers) CUDA_TRY(cudaMallocAsync(&d_sibs, count * layers * 4 * sizeof(u64), st));
-    open_rows_kernel<<<(unsigned)count, 128, 0, st>>>(b->leaves, ll, b->digests, b->shape, d_idx, count, d_rows, d_sibs);
+    open_rows_kernel<<<(unsigned)count, 128, 0, st>>>(b->leaves - b->first_leaf * ll, ll, b->digests, b->shape, d_idx, count, d_rows, d_sibs);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     if (d_rows) CUDA_TRY(cudaMemcpyAsync(rows_out, d_rows, count * ll * sizeof(u64), cudaMemcpyDeviceToHost, st));
@@ -695,7 +820,8 @@ extern "C" int p2b_lde_leaves(p2b_ctx* c, const uint64_t* d_coeffs, uint32_t n_l
   P2B_TRY(ensure_scratch(c, P << n_log));
   ntt::LevelScale sc = lde_scale(n_log);
   for (u64 b = 0; b < ((u64)1 << rate_bits); b++)
-    P2B_TRY(run_lde_block(c, c->stream, d_coeffs, (u64)1 << n_log, c->scratch, n_log, P, b, sc, d_leaves, row_stride, col0));
+    P2B_TRY(run_lde_block(c, c->stream, d_coeffs, (u64)1 << n_log, c->scratch, n_log, P, b, sc, d_leaves, row_stride, col0,
+                          b << n_log));
   return P2B_OK;
 }
 
@@ -712,7 +838,7 @@ extern "C" int p2b_merkle_tree(p2b_ctx* c, const uint64_t* d_leaves, uint64_t nu
   CUDA_TRY(cudaSetDevice(c->device));
   merkle::TreeShape shape = merkle::make_shape(lg, cap_height);
   P2B_TRY(launch_hash_leaves(c, c->stream, d_leaves, row_stride, col_stride, (u32)leaf_len, 0, num_leaves, shape, d_digests, d_cap));
-  return launch_layers(c, c->stream, shape, d_digests, d_cap);
+  return launch_layers(c, c->stream, shape, d_digests, d_cap, 0, num_leaves, 0, nullptr);
 }
 
 extern "C" int p2b_poseidon_permute(p2b_ctx* c, uint64_t* d_states, uint64_t count) {

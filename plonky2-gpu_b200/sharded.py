@@ -1,0 +1,153 @@
+"""Multi-GPU commit: one process per GPU, coset blocks / cap sub-trees sharded over the ranks.
+
+Partition (strong scaling of ONE commit over G ranks, G a power of two, G <= 2^rate_bits):
+  * inverse NTT is per column            -> rank r transforms columns [c0_r, c1_r) of the value matrix,
+  * one exchange step                    -> all-gather of the coefficient columns (NCCL over NVLink),
+  * LDE + leaf hashing + digest layers   -> rank r owns coset blocks [r*R/G, (r+1)*R/G), i.e. the contiguous leaf range
+                                            [r*N/G, (r+1)*N/G); no communication,
+  * cap                                  -> all-gather of each rank's top-layer nodes (32 B each); if those are not yet
+                                            the cap entries (2^cap_height < G) every rank finishes the few top layers.
+The reference has no multi-GPU path (cudaSetDevice(0) only in dead code, cuda/plonky2_gpu.cu:63); the partition follows
+from PolynomialBatch::from_values' own structure: `values.into_par_iter().map(ifft)` (fri/oracle.rs:717-721) and
+fill_digests_buf's independent cap sub-trees (hash/merkle_tree.rs:232-243).
+
+The orchestration is written against two small interfaces so that the host-side logic is testable on CPU with gloo:
+  engine : ifft_columns / commit_blocks / export_top / import_nodes / finish_layers / cap   (GpuEngine = the C ABI)
+  comm   : rank, world, all_gather(array-like) -> list                                      (TorchComm = torch.distributed)
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host-side planning (pure functions)
+# ---------------------------------------------------------------------------------------------------------------
+def column_shard(num_polys, world, rank):
+    """Columns [c0, c1) transformed by `rank`.  Every rank but the last gets ceil(P / world) columns so that the
+    all-gathered (padded) buffer holds the P real columns contiguously at its start."""
+    cmax = -(-num_polys // world)
+    c0 = min(rank * cmax, num_polys)
+    c1 = min(c0 + cmax, num_polys)
+    return c0, c1, cmax
+
+
+def block_shard(rate_bits, world, rank):
+    """Coset blocks [b0, b0 + count) owned by `rank` (block b = leaves [b*n, (b+1)*n))."""
+    R = 1 << rate_bits
+    if world < 1 or world & (world - 1):
+        raise ValueError("world size must be a power of two")
+    if world > R:
+        raise ValueError("world size %d exceeds the 2^rate_bits = %d coset blocks" % (world, R))
+    per = R // world
+    return rank * per, per
+
+
+def local_top_layer(n_log, rate_bits, cap_height, world):
+    """Highest digest layer a rank can compute from its own leaves (0 = leaf digests)."""
+    sub_log = n_log + rate_bits - cap_height
+    span_log = n_log + rate_bits - int(math.log2(world))  # log2(leaves per rank)
+    return min(sub_log, span_log)
+
+
+def node_index(sub_log, sub_digests, layer, Q):
+    """Index (in hashes) of node Q of `layer` inside the reference's digest buffer (merkle_tree.rs:46-54, 424-435);
+    layer == sub_log addresses cap[Q] instead (returned as ('cap', Q))."""
+    if layer == sub_log:
+        return ("cap", Q)
+    bits = sub_log - layer
+    tree, q = Q >> bits, Q & ((1 << bits) - 1)
+    return ("digests", tree * sub_digests + 2 * (((q >> 1) << (layer + 1)) + (1 << layer) - 1) + (q & 1))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# orchestration
+# ---------------------------------------------------------------------------------------------------------------
+def sharded_commit_from_values(engine, comm, values_shard, num_polys, n_log, rate_bits, cap_height):
+    """values_shard: this rank's columns [c0, c1) of the value matrix, engine-native array [cmax][n] (rows beyond
+    c1 - c0 are padding).  Returns the engine's batch handle; afterwards engine.cap(batch) is the full cap on every
+    rank and the batch holds this rank's leaves / digests."""
+    rank, world = comm.rank, comm.world
+    c0, c1, cmax = column_shard(num_polys, world, rank)
+    b0, bcount = block_shard(rate_bits, world, rank)
+    engine.ifft_columns(values_shard, c1 - c0, n_log)                 # in place
+    coeffs_all = comm.all_gather_columns(values_shard, cmax, n_log)   # [world * cmax][n]; first num_polys rows are real
+    batch = engine.commit_blocks(coeffs_all, num_polys, n_log, rate_bits, cap_height, b0, bcount)
+    top = local_top_layer(n_log, rate_bits, cap_height, world)
+    count = ((1 << (n_log + rate_bits)) // world) >> top               # top-layer nodes per rank
+    mine = engine.export_nodes(batch, top, rank * count, count)        # [count][4]
+    everyone = comm.all_gather_nodes(mine, count)                      # [world * count][4], rank-major == node order
+    engine.import_nodes(batch, top, 0, world * count, everyone)
+    engine.finish_layers(batch, top)
+    return batch
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU engine / torch.distributed communicator
+# ---------------------------------------------------------------------------------------------------------------
+class GpuEngine:
+    """The C ABI (libplonky2_b200.so) on torch CUDA tensors (torch is plumbing: device memory + NCCL)."""
+
+    def __init__(self, ctx):
+        import torch
+        from . import lib, _check, PolynomialBatch
+        self.torch, self.lib, self._check, self._PB, self.ctx = torch, lib(), _check, PolynomialBatch, ctx
+
+    def _sync_in(self):
+        self.torch.cuda.current_stream().synchronize()  # torch-side producers done before the library's stream reads
+
+    def ifft_columns(self, t, ncols, n_log):
+        if ncols == 0:
+            return
+        self._sync_in()
+        self._check(self.lib.p2b_ifft_batch(self.ctx.handle, t.data_ptr(), t.data_ptr(), n_log, ncols))
+        self.ctx.synchronize()
+
+    def commit_blocks(self, coeffs, num_polys, n_log, rate_bits, cap_height, b0, bcount):
+        self._sync_in()
+        h = C.c_void_p()
+        self._check(self.lib.p2b_commit_blocks(self.ctx.handle, coeffs.data_ptr(), n_log, num_polys, rate_bits, cap_height,
+                                               None, b0, bcount, C.byref(h)))
+        return self._PB(self.ctx, h.value)
+
+    def export_nodes(self, batch, layer, first, count):
+        out = self.torch.empty((count, 4), dtype=self.torch.int64, device="cuda")
+        self._check(self.lib.p2b_batch_export_nodes(batch.handle, layer, first, count, out.data_ptr()))
+        self.ctx.synchronize()
+        return out
+
+    def import_nodes(self, batch, layer, first, count, t):
+        self._sync_in()
+        self._check(self.lib.p2b_batch_import_nodes(batch.handle, layer, first, count, t.data_ptr()))
+
+    def finish_layers(self, batch, from_layer):
+        self._check(self.lib.p2b_batch_finish_layers(batch.handle, from_layer))
+        self.ctx.synchronize()
+
+    def cap(self, batch):
+        return batch.cap()
+
+
+class TorchComm:
+    """torch.distributed (NCCL on GPUs, gloo on CPU) behind the two collectives the path needs."""
+
+    def __init__(self, dist=None):
+        import torch
+        import torch.distributed as d
+        self.torch, self.dist = torch, dist or d
+        self.rank = self.dist.get_rank() if self.dist.is_initialized() else 0
+        self.world = self.dist.get_world_size() if self.dist.is_initialized() else 1
+
+    def _gather(self, t):
+        if self.world == 1:
+            return t
+        out = self.torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        self.dist.all_gather_into_tensor(out, t.contiguous())
+        return out
+
+    def all_gather_columns(self, t, cmax, n_log):
+        return self._gather(t)
+
+    def all_gather_nodes(self, t, count):
+        return self._gather(t)
