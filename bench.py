@@ -37,6 +37,9 @@ METRIC = "LDE+Merkle commit ms (2^20x135 cols, rate 3)"
 # dynamic thread-instructions of one Poseidon permutation in the shipped SASS (tools/sass_mix.py / ncu
 # smsp__inst_executed of hash_leaves_kernel divided by permutations; profiles/README.md)
 INSTR_PER_PERM = 24500
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE leaf-hash launch (2^20 leaves x 135) from the committed
+# `ncu --set full` capture, profiles/r01_hash_leaves_ncu.md
+HASH_LAUNCH_DRAM_BYTES_2P20_X135 = 1259251000 + 34948096
 INT_LANES_PER_CLK_PER_SM = 64  # measured IADD3 / IMAD issue rate on B200 (tools/int_peak.cu, profiles/int_peak_r01.md)
 
 
@@ -316,7 +319,8 @@ def run_b200(args, rank, world, local_rank):
                     "steps": e2e_steps, "note": "pinned host values -> p2b_commit_from_values -> D2H coefficients + cap; host wall clock, max over ranks"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "merkle::hash_leaves_kernel", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"],
-                         "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind + " (burst copy bandwidth)",
+                         "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"],
+                         "traffic": HASH_LAUNCH_DRAM_BYTES_2P20_X135 if (n_log == 20 and P == 135) else None, "peak_source": peak_kind + " (burst copy bandwidth)",
                          "launches_timed": hash_launches, "avg_launch_ms": avg_hash_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "share_of_step": hash_ms / max(dev_ms, 1e-9)},
             "roofline_int": {"bound": "integer issue (64 INT32 lanes/clk/SM measured)", "achieved": int_ach / 1e12, "peak": int_peak / 1e12,
