@@ -138,6 +138,48 @@ int p2b_batch_import_nodes(p2b_batch* b, uint32_t layer, uint64_t node_first, ui
 int p2b_batch_finish_layers(p2b_batch* b, uint32_t from_layer);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Quotient polynomials: compute_quotient_polys (plonky2/src/plonk/prover.rs:790-1034) for a circuit given as data.
+ * The reference CUDA kernel hard-codes one circuit (cuda/plonky2_gpu_impl.cuh:600-685, plonky2_gpu.cu:665-689); here
+ * the host passes the part of CommonCircuitData the evaluation reads (circuit_data.rs:270-349).
+ *   gates[i]   : `common_data.gates[i]` -- type, its selector polynomial index and group range
+ *                (SelectorsInfo, gates/selectors.rs:13-23) and the gate's own parameters:
+ *                  NOOP -, CONSTANT p0=num_consts, PUBLIC_INPUT -, ARITHMETIC p0=num_ops, BASE_SUM p0=num_limbs p1=B,
+ *                  POSEIDON -, RANDOM_ACCESS p0=bits p1=num_copies p2=num_extra_constants, U32_ARITHMETIC p0=num_ops,
+ *                  U32_ADD_MANY p0=num_addends p1=num_ops, U32_RANGE_CHECK p0=num_input_limbs, U32_SUBTRACTION p0=num_ops,
+ *                  COMPARISON p0=num_bits p1=num_chunks
+ *   rows       : the three commitments' leaf rows as the commit produces them (row L = LDE point reverse_bits(L)):
+ *                wires [num_wires..], zs_partial_products [num_challenges * (1 + num_partial_products)..],
+ *                constants_sigmas [num_constants + num_routed_wires..]; trailing salt columns are ignored.
+ * Outputs (device, either may be NULL): values [num_challenges][n * 2^ceil(log2 qdf)] = the quotient evaluations on the
+ * coset (prover.rs:884-1012), coeffs = their coset_ifft (prover.rs:1014-1021), both canonical.
+ * ------------------------------------------------------------------------------------------------- */
+enum {
+  P2B_GATE_NOOP = 0, P2B_GATE_CONSTANT = 1, P2B_GATE_PUBLIC_INPUT = 2, P2B_GATE_ARITHMETIC = 3, P2B_GATE_BASE_SUM = 4,
+  P2B_GATE_POSEIDON = 5, P2B_GATE_RANDOM_ACCESS = 6, P2B_GATE_U32_ARITHMETIC = 7, P2B_GATE_U32_ADD_MANY = 8,
+  P2B_GATE_U32_RANGE_CHECK = 9, P2B_GATE_U32_SUBTRACTION = 10, P2B_GATE_COMPARISON = 11
+};
+typedef struct {
+  uint32_t type, selector_index, group_start, group_end; /* group = gate index range [start, end) of its selector */
+  uint32_t p0, p1, p2, reserved;
+} p2b_gate;
+typedef struct {
+  uint32_t degree_bits, rate_bits, quotient_degree_factor, num_challenges;
+  uint32_t num_wires, num_routed_wires, num_constants, num_selectors;
+  uint32_t num_gates, reserved;
+  const p2b_gate* gates;  /* host */
+  const uint64_t* k_is;   /* host [num_routed_wires]: common_data.k_is */
+} p2b_circuit;
+
+int p2b_quotient_polys(p2b_ctx* ctx, const p2b_circuit* circuit, const p2b_batch* wires, const p2b_batch* zs_partial_products,
+                       const p2b_batch* constants_sigmas, const uint64_t* public_inputs_hash /* host [4] */,
+                       const uint64_t* betas, const uint64_t* gammas, const uint64_t* alphas /* host [num_challenges] */,
+                       uint64_t* d_values_out, uint64_t* d_coeffs_out);
+int p2b_quotient_polys_rows(p2b_ctx* ctx, const p2b_circuit* circuit, const uint64_t* d_wires_rows, uint64_t wires_stride,
+                            const uint64_t* d_zs_pp_rows, uint64_t zs_pp_stride, const uint64_t* d_consts_sigmas_rows,
+                            uint64_t consts_sigmas_stride, const uint64_t* public_inputs_hash, const uint64_t* betas,
+                            const uint64_t* gammas, const uint64_t* alphas, uint64_t* d_values_out, uint64_t* d_coeffs_out);
+
+/* ---------------------------------------------------------------------------------------------------
  * Building blocks (device pointers unless stated).  Each mirrors one reference function.
  * ------------------------------------------------------------------------------------------------- */
 /* values.into_par_iter().map(|v| v.ifft())  (fri/oracle.rs:717-721, field/src/fft.rs:73-103).

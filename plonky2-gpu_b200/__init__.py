@@ -47,6 +47,45 @@ class BatchInfo(C.Structure):
                 ("leaf_len", C.c_uint64), ("num_digests", C.c_uint64)]
 
 
+class Gate(C.Structure):
+    """p2b_gate (include/plonky2_b200.h): one entry of common_data.gates with its selector group."""
+    _fields_ = [("type", C.c_uint32), ("selector_index", C.c_uint32), ("group_start", C.c_uint32), ("group_end", C.c_uint32),
+                ("p0", C.c_uint32), ("p1", C.c_uint32), ("p2", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class CircuitStruct(C.Structure):
+    _fields_ = [("degree_bits", C.c_uint32), ("rate_bits", C.c_uint32), ("quotient_degree_factor", C.c_uint32),
+                ("num_challenges", C.c_uint32), ("num_wires", C.c_uint32), ("num_routed_wires", C.c_uint32),
+                ("num_constants", C.c_uint32), ("num_selectors", C.c_uint32), ("num_gates", C.c_uint32), ("reserved", C.c_uint32),
+                ("gates", C.POINTER(Gate)), ("k_is", C.POINTER(C.c_uint64))]
+
+
+GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_BASE_SUM, GATE_POSEIDON, GATE_RANDOM_ACCESS = range(7)
+GATE_U32_ARITHMETIC, GATE_U32_ADD_MANY, GATE_U32_RANGE_CHECK, GATE_U32_SUBTRACTION, GATE_COMPARISON = range(7, 12)
+
+
+class Circuit:
+    """The part of CommonCircuitData that compute_quotient_polys reads (plonk/circuit_data.rs:270-349).
+    gates: list of (type, params tuple); selector_indices[i], groups[selector] = (start, end) as SelectorsInfo."""
+
+    def __init__(self, gates, selector_indices, groups, num_wires, num_routed_wires, num_constants, k_is, degree_bits,
+                 rate_bits=3, num_challenges=2, quotient_degree_factor=8):
+        self._gates = (Gate * max(len(gates), 1))()
+        for i, (t, params) in enumerate(gates):
+            pr = list(params) + [0, 0, 0]
+            g0, g1 = groups[selector_indices[i]]
+            self._gates[i] = Gate(t, selector_indices[i], g0, g1, pr[0], pr[1], pr[2], 0)
+        self._kis = (C.c_uint64 * max(num_routed_wires, 1))(*[int(k) % ORDER for k in k_is])
+        self.struct = CircuitStruct(degree_bits, rate_bits, quotient_degree_factor, num_challenges, num_wires, num_routed_wires,
+                                    num_constants, len(groups), len(gates), 0, self._gates, self._kis)
+        self.num_challenges, self.degree_bits = num_challenges, degree_bits
+        self.quotient_degree_bits = (quotient_degree_factor - 1).bit_length()
+
+    @property
+    def lde_size(self):
+        return 1 << (self.degree_bits + self.quotient_degree_bits)
+
+
 class RustError(C.Structure):
     _fields_ = [("code", C.c_int), ("message", C.c_void_p)]
 
@@ -90,6 +129,8 @@ def lib():
         "p2b_batch_export_nodes": (i, [vp, u32, u64, u64, vp]),
         "p2b_batch_import_nodes": (i, [vp, u32, u64, u64, vp]),
         "p2b_batch_finish_layers": (i, [vp, u32]),
+        "p2b_quotient_polys": (i, [vp, C.POINTER(CircuitStruct), vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "p2b_quotient_polys_rows": (i, [vp, C.POINTER(CircuitStruct), vp, u64, vp, u64, vp, u64, vp, vp, vp, vp, vp, vp]),
         "p2b_ifft_batch": (i, [vp, vp, vp, u32, u64]),
         "p2b_lde_leaves": (i, [vp, vp, u32, u64, u32, vp, u64, u64]),
         "p2b_merkle_tree": (i, [vp, vp, u64, u64, u64, u64, u32, vp, vp]),
@@ -267,6 +308,18 @@ class Context:
 
     def fill_synthetic(self, dbuf, count, seed, first_index=0):
         _check(lib().p2b_fill_synthetic(self.handle, dbuf.ptr, count, seed, first_index))
+
+
+def compute_quotient_polys(ctx, circuit, wires, zs_partial_products, constants_sigmas, public_inputs_hash, betas, gammas, alphas):
+    """compute_quotient_polys (plonk/prover.rs:790-1034) on three committed PolynomialBatch objects.
+    Returns (values [num_challenges][lde_size], coeffs [num_challenges][lde_size]) as numpy arrays."""
+    nc, size = circuit.num_challenges, circuit.lde_size
+    dv, dc = DeviceBuffer(ctx, nc * size), DeviceBuffer(ctx, nc * size)
+    arr = lambda x, n: (C.c_uint64 * n)(*[int(v) % ORDER for v in x])
+    _check(lib().p2b_quotient_polys(ctx.handle, C.byref(circuit.struct), wires.handle, zs_partial_products.handle, constants_sigmas.handle,
+                                    arr(public_inputs_hash, 4), arr(betas, nc), arr(gammas, nc), arr(alphas, nc), dv.ptr, dc.ptr))
+    ctx.synchronize()
+    return dv.to_host().reshape(nc, size), dc.to_host().reshape(nc, size)
 
 
 class MerkleTree:

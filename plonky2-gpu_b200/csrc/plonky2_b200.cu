@@ -28,6 +28,7 @@
 #include "../../include/plonky2_b200.h"
 #include "merkle.cuh"
 #include "ntt.cuh"
+#include "quotient.cuh"
 
 using gl::u32;
 using gl::u64;
@@ -947,6 +948,160 @@ extern "C" int p2b_timer_stop_ms(p2b_ctx* c, float* ms_out) {
   CUDA_TRY(cudaEventSynchronize(c->ev_t1));
   CUDA_TRY(cudaEventElapsedTime(ms_out, c->ev_t0, c->ev_t1));
   return P2B_OK;
+}
+
+// ======================================================================================================
+// quotient polynomials (plonky2/src/plonk/prover.rs:790-1034)
+// ======================================================================================================
+static int quotient_impl(p2b_ctx* c, const p2b_circuit* circ, const u64* d_wires, u64 wires_stride, const u64* d_zs_pp,
+                         u64 zs_stride, const u64* d_cs, u64 cs_stride, const u64* pih, const u64* betas, const u64* gammas,
+                         const u64* alphas, u64* d_values_out, u64* d_coeffs_out, u64* d_rows_out) {
+  if (!c || !circ || !d_wires || !d_zs_pp || !d_cs || !pih || !betas || !gammas || !alphas) return fail(P2B_ERR_INVALID, "NULL argument");
+  if (!circ->gates && circ->num_gates) return fail(P2B_ERR_INVALID, "NULL gate list");
+  if (!circ->k_is && circ->num_routed_wires) return fail(P2B_ERR_INVALID, "NULL k_is");
+  const u32 nc = circ->num_challenges, qdf = circ->quotient_degree_factor;
+  if (nc == 0 || nc > quotient::MAX_CHALLENGES) return fail(P2B_ERR_INVALID, "num_challenges must be 1..%d", quotient::MAX_CHALLENGES);
+  if (qdf < 2) return fail(P2B_ERR_INVALID, "quotient_degree_factor must be at least 2");
+  u32 qdb = 0;
+  while ((1u << qdb) < qdf) qdb++;  // log2_ceil
+  if (qdb > circ->rate_bits)
+    return fail(P2B_ERR_UNSUPPORTED, "constraints of degree higher than the rate are not supported (prover.rs:809-813)");
+  if ((1u << qdb) > quotient::MAX_ZH) return fail(P2B_ERR_UNSUPPORTED, "quotient degree factor too large");
+  if (circ->degree_bits + circ->rate_bits > 32) return fail(P2B_ERR_INVALID, "degree_bits + rate_bits exceeds two-adicity");
+  if (circ->num_selectors > circ->num_constants) return fail(P2B_ERR_INVALID, "more selectors than constants");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+
+  quotient::Params p{};
+  p.degree_bits = circ->degree_bits;
+  p.rate_bits = circ->rate_bits;
+  p.qdb = qdb;
+  p.num_challenges = nc;
+  p.num_wires = circ->num_wires;
+  p.num_routed = circ->num_routed_wires;
+  p.num_constants = circ->num_constants;
+  p.num_selectors = circ->num_selectors;
+  p.max_degree = qdf;
+  p.num_partial_products = (circ->num_routed_wires + qdf - 1) / qdf - 1;  // partial_products.rs:40-47
+  if (circ->num_routed_wires == 0) p.num_partial_products = 0;
+  p.num_gates = circ->num_gates;
+  u32 ngc = 0;
+  std::vector<quotient::GateDesc> gates(circ->num_gates);
+  for (u32 i = 0; i < circ->num_gates; i++) {
+    const p2b_gate& g = circ->gates[i];
+    if (g.type >= quotient::G_NUM_TYPES) return fail(P2B_ERR_UNSUPPORTED, "gate %u: unknown gate type %u", i, g.type);
+    if (g.selector_index >= circ->num_selectors || g.group_start > i || g.group_end <= i || g.group_end > circ->num_gates)
+      return fail(P2B_ERR_INVALID, "gate %u: bad selector group", i);
+    if (g.type == quotient::G_RANDOM_ACCESS && g.p0 > 6) return fail(P2B_ERR_UNSUPPORTED, "RandomAccessGate with more than 6 bits");
+    if (g.type == quotient::G_COMPARISON && g.p1 == 0) return fail(P2B_ERR_INVALID, "ComparisonGate with zero chunks");
+    gates[i] = quotient::GateDesc{g.type, g.selector_index, g.group_start, g.group_end, g.p0, g.p1, g.p2, 0};
+    u32 k = quotient::gate_num_constraints(gates[i]);
+    ngc = k > ngc ? k : ngc;
+  }
+  p.num_gate_constraints = ngc;
+  p.num_terms = nc * (p.num_partial_products + 2) + ngc;
+  for (int i = 0; i < 4; i++) p.pih[i] = pih[i] % gl::P;
+  for (u32 i = 0; i < nc; i++) {
+    p.betas[i] = betas[i] % gl::P;
+    p.gammas[i] = gammas[i] % gl::P;
+  }
+  // ZeroPolyOnCoset::new (zero_poly_coset.rs:20-33)
+  {
+    u64 g_pow_n = hostf::pow(hostf::COSET_SHIFT, (u64)1 << circ->degree_bits);
+    u64 v = hostf::root(qdb), cur = 1;
+    for (u32 i = 0; i < (1u << qdb); i++) {
+      u64 gv = hostf::mul(g_pow_n, cur);
+      p.zh[i] = gv ? gv - 1 : gl::P - 1;  // g^n * v^i - 1 (no u64 overflow)
+      p.zh_inv[i] = hostf::inv(p.zh[i]);
+      cur = hostf::mul(cur, v);
+    }
+  }
+  p.w = hostf::root(circ->degree_bits + qdb);
+  p.n_field = ((u64)1 << circ->degree_bits) % gl::P;
+  p.wires = d_wires;
+  p.wires_stride = wires_stride;
+  p.zs_pp = d_zs_pp;
+  p.zs_stride = zs_stride;
+  p.cs = d_cs;
+  p.cs_stride = cs_stride;
+
+  const u32 lde_log = circ->degree_bits + qdb;
+  const u64 lde_size = (u64)1 << lde_log;
+  quotient::GateDesc* d_gates = nullptr;
+  u64 *d_kis = nullptr, *d_alphas = nullptr, *d_apows = nullptr, *d_vals = nullptr;
+  auto body = [&]() -> int {
+    CUDA_TRY(cudaMallocAsync(&d_gates, (gates.size() ? gates.size() : 1) * sizeof(quotient::GateDesc), st));
+    if (!gates.empty()) CUDA_TRY(cudaMemcpyAsync(d_gates, gates.data(), gates.size() * sizeof(quotient::GateDesc), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMallocAsync(&d_kis, (p.num_routed ? p.num_routed : 1) * sizeof(u64), st));
+    if (p.num_routed) CUDA_TRY(cudaMemcpyAsync(d_kis, circ->k_is, p.num_routed * sizeof(u64), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMallocAsync(&d_alphas, nc * sizeof(u64), st));
+    u64 ha[quotient::MAX_CHALLENGES];
+    for (u32 i = 0; i < nc; i++) ha[i] = alphas[i] % gl::P;
+    CUDA_TRY(cudaMemcpyAsync(d_alphas, ha, nc * sizeof(u64), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));  // host staging buffers (gates, ha) go out of scope
+    CUDA_TRY(cudaMallocAsync(&d_apows, (u64)nc * p.num_terms * sizeof(u64), st));
+    quotient::alpha_pows_kernel<<<(p.num_terms + 127) / 128, 128, 0, st>>>(d_apows, p.num_terms, nc, d_alphas);
+    c->launches++;
+    u64* vals = d_values_out;
+    if (!vals) {
+      CUDA_TRY(cudaMallocAsync(&d_vals, nc * lde_size * sizeof(u64), st));
+      vals = d_vals;
+    }
+    p.gates = d_gates;
+    p.k_is = d_kis;
+    p.alpha_pows = d_apows;
+    p.out_values = vals;
+    p.out_rows = d_rows_out;
+    quotient::quotient_values_kernel<<<(unsigned)((lde_size + 127) / 128), 128, 0, st>>>(p);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (d_coeffs_out) {
+      // coset_ifft(F::coset_shift()) per challenge (prover.rs:1014-1021, polynomial/mod.rs:64-77)
+      Plan pl = make_plan(lde_log);
+      u64* tmp = d_coeffs_out;
+      if (pl.n_strided) {
+        P2B_TRY(ensure_scratch(c, nc * lde_size));
+        tmp = c->scratch;
+      }
+      P2B_TRY(run_ifft(c, vals, d_coeffs_out, tmp, lde_log, nc));
+      quotient::scale_by_powers_kernel<<<(unsigned)((lde_size + 255) / 256), 256, 0, st>>>(d_coeffs_out, lde_size, nc,
+                                                                                     hostf::inv(hostf::COSET_SHIFT));
+      c->launches++;
+      CUDA_TRY(cudaGetLastError());
+    }
+    return P2B_OK;
+  };
+  int rc = body();
+  for (void* ptr : {(void*)d_gates, (void*)d_kis, (void*)d_alphas, (void*)d_apows, (void*)d_vals})
+    if (ptr) cudaFreeAsync(ptr, st);
+  return rc;
+}
+
+extern "C" int p2b_quotient_polys_rows(p2b_ctx* ctx, const p2b_circuit* circuit, const uint64_t* d_wires_rows, uint64_t wires_stride,
+                                       const uint64_t* d_zs_pp_rows, uint64_t zs_pp_stride, const uint64_t* d_consts_sigmas_rows,
+                                       uint64_t consts_sigmas_stride, const uint64_t* public_inputs_hash, const uint64_t* betas,
+                                       const uint64_t* gammas, const uint64_t* alphas, uint64_t* d_values_out, uint64_t* d_coeffs_out) {
+  return quotient_impl(ctx, circuit, d_wires_rows, wires_stride, d_zs_pp_rows, zs_pp_stride, d_consts_sigmas_rows, consts_sigmas_stride,
+                       public_inputs_hash, betas, gammas, alphas, d_values_out, d_coeffs_out, nullptr);
+}
+
+extern "C" int p2b_quotient_polys(p2b_ctx* ctx, const p2b_circuit* circuit, const p2b_batch* wires, const p2b_batch* zs_pp,
+                                  const p2b_batch* consts_sigmas, const uint64_t* public_inputs_hash, const uint64_t* betas,
+                                  const uint64_t* gammas, const uint64_t* alphas, uint64_t* d_values_out, uint64_t* d_coeffs_out) {
+  if (!circuit || !wires || !zs_pp || !consts_sigmas) return fail(P2B_ERR_INVALID, "NULL argument");
+  for (const p2b_batch* b : {wires, zs_pp, consts_sigmas}) {
+    if (b->info.degree_log != circuit->degree_bits || b->info.rate_bits != circuit->rate_bits)
+      return fail(P2B_ERR_INVALID, "batch shape does not match the circuit (degree_bits / rate_bits)");
+    if (b->local_leaves != b->info.num_leaves) return fail(P2B_ERR_UNSUPPORTED, "sharded batches: gather the rows first");
+  }
+  u32 qdf = circuit->quotient_degree_factor;
+  u64 npp = circuit->num_routed_wires ? (circuit->num_routed_wires + qdf - 1) / (qdf ? qdf : 1) - 1 : 0;
+  if (wires->info.num_polys < circuit->num_wires) return fail(P2B_ERR_INVALID, "wires batch has fewer columns than num_wires");
+  if (consts_sigmas->info.num_polys < (u64)circuit->num_constants + circuit->num_routed_wires)
+    return fail(P2B_ERR_INVALID, "constants/sigmas batch has too few columns");
+  if (zs_pp->info.num_polys < (u64)circuit->num_challenges * (1 + npp)) return fail(P2B_ERR_INVALID, "zs/partial-products batch has too few columns");
+  return quotient_impl(ctx, circuit, wires->leaves, wires->info.leaf_len, zs_pp->leaves, zs_pp->info.leaf_len, consts_sigmas->leaves,
+                       consts_sigmas->info.leaf_len, public_inputs_hash, betas, gammas, alphas, d_values_out, d_coeffs_out, nullptr);
 }
 
 #include "compat.cuh"

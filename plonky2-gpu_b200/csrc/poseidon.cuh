@@ -181,6 +181,67 @@ __device__ __forceinline__ void round_sync() {
 #endif
 }
 
+// mds_partial_layer_init (poseidon.rs:310-337): s[0] unchanged; s[c] = sum_r s[r] * init[r-1][c-1].
+// Rolled over the output column c (keeps ~24 KB of straight-line code out of the instruction cache); the results
+// are pushed through a shift register so no register array is indexed dynamically.
+__device__ __forceinline__ void partial_layer_init(u64 (&s)[12]) {
+#ifdef P2B_INIT_UNROLLED
+  u64 t[12];
+  t[0] = s[0];
+#pragma unroll
+  for (int c = 1; c < 12; c++) {
+    u64 lo = 0, hi = 0;
+    u32 top = 0;
+#pragma unroll
+    for (int r = 1; r < 12; r++) mac160(lo, hi, top, s[r], C.init[(r - 1) * 11 + (c - 1)]);
+    t[c] = reduce160(lo, hi, top);
+  }
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = t[i];
+#else
+  u64 t[12];
+#pragma unroll
+  for (int i = 1; i < 12; i++) t[i] = 0;
+#pragma unroll 1
+  for (int c = 0; c < 11; c++) {
+    u64 lo = 0, hi = 0;
+    u32 top = 0;
+#pragma unroll
+    for (int r = 1; r < 12; r++) mac160(lo, hi, top, s[r], C.init[(r - 1) * 11 + c]);
+    u64 v = reduce160(lo, hi, top);
+#pragma unroll
+    for (int i = 1; i < 11; i++) t[i] = t[i + 1];
+    t[11] = v;
+  }
+#pragma unroll
+  for (int i = 1; i < 12; i++) s[i] = t[i];
+#endif
+}
+
+// mds_partial_layer_fast (poseidon.rs:398-427) for partial round r; s0 = the S-boxed (and constant-added) lane 0:
+//   s[0] <- 25*s0 + sum_i w_hat[r][i-1] * s[i]   (u160 accumulator),   s[i] <- s[i] + s0 * vs[r][i-1]
+__device__ __forceinline__ void partial_layer_fast(u64 (&s)[12], u64 s0, int r) {
+  u64 lo, hi;
+  u32 top = 0;
+  {
+    u32 a0, a1;
+    gl::split(s0, a0, a1);
+    u64 pl = (u64)a0 * (mds_circ(0) + MDS_DIAG0), ph = (u64)a1 * (mds_circ(0) + MDS_DIAG0);
+    u32 pl0, pl1, ph0, ph1, m1, m2;
+    gl::split(pl, pl0, pl1);
+    gl::split(ph, ph0, ph1);
+    asm("{ add.cc.u32 %0, %2, %3; addc.u32 %1, %4, 0; }" : "=&r"(m1), "=&r"(m2) : "r"(pl1), "r"(ph0), "r"(ph1));
+    lo = gl::pack(pl0, m1);
+    hi = (u64)m2;
+  }
+#pragma unroll
+  for (int i = 1; i < 12; i++) mac160(lo, hi, top, s[i], C.w_hats[r * 11 + i - 1]);
+  u64 d = reduce160(lo, hi, top);
+#pragma unroll
+  for (int i = 1; i < 12; i++) s[i] = gl::mul_add(s0, C.vs[r * 11 + i - 1], s[i]);
+  s[0] = d;
+}
+
 // The permutation.  Input: any u64 representatives; output: u64 representatives (NOT canonicalised --
 // callers canonicalise what they store).
 __device__ __forceinline__ void permute(u64 (&s)[12]) {
@@ -198,66 +259,12 @@ __device__ __forceinline__ void permute(u64 (&s)[12]) {
     }
     if (half == 0) {
       // ---- partial rounds (poseidon.rs:574-588); first-round constants were folded into post[3] ----
-      {
-        // mds_partial_layer_init (poseidon.rs:310-337): t[0] = s[0]; t[c] = sum_r s[r] * init[r-1][c-1]
-#ifdef P2B_INIT_UNROLLED
-        u64 t[12];
-        t[0] = s[0];
-#pragma unroll
-        for (int c = 1; c < 12; c++) {
-          u64 lo = 0, hi = 0;
-          u32 top = 0;
-#pragma unroll
-          for (int r = 1; r < 12; r++) mac160(lo, hi, top, s[r], C.init[(r - 1) * 11 + (c - 1)]);
-          t[c] = reduce160(lo, hi, top);
-        }
-#pragma unroll
-        for (int i = 0; i < 12; i++) s[i] = t[i];
-#else
-        // rolled over the output column c (keeps ~24 KB of straight-line code out of the instruction cache); the
-        // results are pushed through a shift register so no register array is indexed dynamically.
-        u64 t[12];
-#pragma unroll
-        for (int i = 1; i < 12; i++) t[i] = 0;
-#pragma unroll 1
-        for (int c = 0; c < 11; c++) {
-          u64 lo = 0, hi = 0;
-          u32 top = 0;
-#pragma unroll
-          for (int r = 1; r < 12; r++) mac160(lo, hi, top, s[r], C.init[(r - 1) * 11 + c]);
-          u64 v = reduce160(lo, hi, top);
-#pragma unroll
-          for (int i = 1; i < 11; i++) t[i] = t[i + 1];
-          t[11] = v;
-        }
-#pragma unroll
-        for (int i = 1; i < 12; i++) s[i] = t[i];
-#endif
-      }
+      partial_layer_init(s);
 #pragma unroll 1
       for (int r = 0; r < 22; r++) {
         round_sync();
         u64 s0 = gl::add_canonical(sbox(s[0]), C.partial_rc[r]);
-        // mds_partial_layer_fast (poseidon.rs:398-427): d = 25*s0 + sum w_hat[i-1]*s[i]  (u160 accumulator)
-        u64 lo, hi;
-        u32 top = 0;
-        {
-          u32 a0, a1;
-          gl::split(s0, a0, a1);
-          u64 pl = (u64)a0 * (mds_circ(0) + MDS_DIAG0), ph = (u64)a1 * (mds_circ(0) + MDS_DIAG0);
-          u32 pl0, pl1, ph0, ph1, m1, m2;
-          gl::split(pl, pl0, pl1);
-          gl::split(ph, ph0, ph1);
-          asm("{ add.cc.u32 %0, %2, %3; addc.u32 %1, %4, 0; }" : "=&r"(m1), "=&r"(m2) : "r"(pl1), "r"(ph0), "r"(ph1));
-          lo = gl::pack(pl0, m1);
-          hi = (u64)m2;
-        }
-#pragma unroll
-        for (int i = 1; i < 12; i++) mac160(lo, hi, top, s[i], C.w_hats[r * 11 + i - 1]);
-        u64 d = reduce160(lo, hi, top);
-#pragma unroll
-        for (int i = 1; i < 12; i++) s[i] = gl::mul_add(s0, C.vs[r * 11 + i - 1], s[i]);
-        s[0] = d;
+        partial_layer_fast(s, s0, r);
       }
       // constant layer of round 26 (first of the closing full rounds)
 #pragma unroll

@@ -1,0 +1,453 @@
+// quotient.cuh -- quotient-polynomial evaluation over the LDE domain for any gate set.
+//
+// Reference (CPU):  compute_quotient_polys                 plonky2/src/plonk/prover.rs:790-1034
+//                   eval_vanishing_poly_base_batch         plonky2/src/plonk/vanishing_poly.rs:100-226
+//                   evaluate_gate_constraints_base_batch   vanishing_poly.rs:267-306, gates/gate.rs:113-150, 261-268
+//                   check_partial_products                 util/partial_products.rs:52-78
+//                   reduce_with_powers_multi               plonk/plonk_common.rs:97-114
+//                   ZeroPolyOnCoset                        field/src/zero_poly_coset.rs:7-60
+// Reference (GPU):  compute_quotient_values_kernel, cuda/plonky2_gpu_impl.cuh:485-878 -- hard-coded to one ed25519
+//                   circuit (25 literal gate instances, 231 constraints, literal public-input hash); this kernel takes
+//                   the circuit as data (p2b_circuit) instead.
+//
+// One thread per LDE point i (x = g * w^i).  It reads its three leaf rows (leaf index = reverse_bits(i * step), the
+// layout the commit kernels produce), evaluates every gate's constraints, and folds each term straight into the
+// per-challenge sums  sum_t alpha_c^t * term_t  with a table of alpha powers -- the same value as the reference's
+// Horner pass from the last term (exact field arithmetic), without the 231-word per-thread constraint array the
+// reference keeps in local memory:  gate constraint j of gate g contributes filter_g * alpha^(T0 + j) * c_{g,j}, so a
+// gate accumulates sum_j alpha^(T0+j) c_{g,j} and is multiplied by its filter once.
+#pragma once
+#include "poseidon.cuh"
+
+namespace quotient {
+
+using gl::u32;
+using gl::u64;
+
+enum GateType : u32 {
+  G_NOOP = 0, G_CONSTANT = 1, G_PUBLIC_INPUT = 2, G_ARITHMETIC = 3, G_BASE_SUM = 4, G_POSEIDON = 5, G_RANDOM_ACCESS = 6,
+  G_U32_ARITHMETIC = 7, G_U32_ADD_MANY = 8, G_U32_RANGE_CHECK = 9, G_U32_SUBTRACTION = 10, G_COMPARISON = 11, G_NUM_TYPES = 12
+};
+
+struct GateDesc {  // == p2b_gate
+  u32 type, selector_index, group_start, group_end, p0, p1, p2, reserved;
+};
+
+static constexpr int MAX_CHALLENGES = 4;
+static constexpr int MAX_ZH = 32;
+
+struct Params {
+  u32 degree_bits, rate_bits, qdb, num_challenges;
+  u32 num_wires, num_routed, num_constants, num_selectors, num_partial_products, max_degree, num_gates, num_gate_constraints;
+  const u64* wires; u64 wires_stride;   // leaf rows of the three commitments
+  const u64* zs_pp; u64 zs_stride;
+  const u64* cs; u64 cs_stride;
+  const GateDesc* gates;                // device
+  const u64* k_is;                      // device [num_routed]
+  const u64* alpha_pows;                // device [num_challenges][num_terms]
+  u32 num_terms;
+  u64 pih[4];
+  u64 betas[MAX_CHALLENGES], gammas[MAX_CHALLENGES];
+  u64 zh[MAX_ZH], zh_inv[MAX_ZH];       // Z_H on the coset and inverses, indexed i mod 2^qdb
+  u64 w;                                // generator of the evaluation subgroup (order 2^(degree_bits + qdb))
+  u64 n_field;                          // n as a field element
+  u64* out_values;                      // [num_challenges][lde_size]
+  u64* out_rows;                        // optional [lde_size][num_challenges] (the reference's d_outs layout)
+};
+
+// host: number of constraints of a gate (each gate's num_constraints())
+__host__ __device__ inline u32 gate_num_constraints(const GateDesc& g) {
+  switch (g.type) {
+    case G_NOOP: return 0;
+    case G_CONSTANT: return g.p0;
+    case G_PUBLIC_INPUT: return 4;
+    case G_ARITHMETIC: return g.p0;
+    case G_BASE_SUM: return 1 + g.p0;
+    case G_POSEIDON: return 123;
+    case G_RANDOM_ACCESS: return (g.p0 + 2) * g.p1 + g.p2;
+    case G_U32_ARITHMETIC: return g.p0 * 36;
+    case G_U32_ADD_MANY: return g.p1 * 21;
+    case G_U32_RANGE_CHECK: return g.p0 * 17;
+    case G_U32_SUBTRACTION: return g.p0 * 19;
+    case G_COMPARISON: return 6 + 5 * g.p1 + (g.p0 + g.p1 - 1) / g.p1;
+    default: return 0;
+  }
+}
+
+// Accumulates sum_j alpha_c^(base + j) * c_j for every challenge; emit() is called in constraint order.
+struct Emitter {
+  u64 acc[MAX_CHALLENGES];
+  const u64* ap;  // alpha_pows + base
+  u32 stride, nc, j;
+  __device__ __forceinline__ void init(const u64* alpha_pows, u32 num_terms, u32 base, u32 nc_) {
+    ap = alpha_pows + base;
+    stride = num_terms;
+    nc = nc_;
+    j = 0;
+#pragma unroll
+    for (int c = 0; c < MAX_CHALLENGES; c++) acc[c] = 0;
+  }
+  __device__ __forceinline__ void emit(u64 v) {
+#pragma unroll
+    for (int c = 0; c < MAX_CHALLENGES; c++)
+      if ((u32)c < nc) acc[c] = gl::mul_add(v, __ldg(ap + (u64)c * stride + j), acc[c]);
+    j++;
+  }
+};
+
+__device__ __forceinline__ u64 fsub(u64 a, u64 b) { return gl::sub(a, b); }
+__device__ __forceinline__ u64 fadd(u64 a, u64 b) { return gl::add(a, b); }
+__device__ __forceinline__ u64 fmul(u64 a, u64 b) { return gl::mul(a, b); }
+
+// prod_{x < m} (limb - x)
+__device__ __forceinline__ u64 range_product(u64 limb, u32 m) {
+  u64 p = limb;
+  for (u32 x = 1; x < m; x++) p = fmul(p, fsub(limb, x));
+  return p;
+}
+
+// ---- gates (wires: W[k], constants after the selector prefix: K[k]) ----------------------------------------------
+#define W(k) __ldg(w + (k))
+#define K(k) __ldg(kc + (k))
+
+__device__ __forceinline__ void eval_constant(const GateDesc& g, const u64* w, const u64* kc, Emitter& e) {  // constant.rs:150-158
+  for (u32 i = 0; i < g.p0; i++) e.emit(fsub(K(i), W(i)));
+}
+__device__ __forceinline__ void eval_public_input(const u64* w, const u64* pih, Emitter& e) {  // public_input.rs:129-139
+  for (u32 i = 0; i < 4; i++) e.emit(fsub(W(i), pih[i]));
+}
+__device__ __forceinline__ void eval_arithmetic(const GateDesc& g, const u64* w, const u64* kc, Emitter& e) {  // arithmetic_base.rs:199-220
+  u64 c0 = K(0), c1 = K(1);
+  for (u32 i = 0; i < g.p0; i++) {
+    u64 computed = fadd(fmul(fmul(W(4 * i), W(4 * i + 1)), c0), fmul(W(4 * i + 2), c1));
+    e.emit(fsub(W(4 * i + 3), computed));
+  }
+}
+__device__ __forceinline__ void eval_base_sum(const GateDesc& g, const u64* w, Emitter& e) {  // base_sum.rs:213-230
+  const u32 nl = g.p0, B = g.p1;
+  u64 sum = 0;
+  for (u32 i = nl; i-- > 0;) sum = fadd(fmul(sum, B), W(1 + i));
+  e.emit(fsub(sum, W(0)));
+  for (u32 i = 0; i < nl; i++) e.emit(range_product(W(1 + i), B));
+}
+__device__ __forceinline__ void eval_random_access(const GateDesc& g, const u64* w, const u64* kc, Emitter& e) {  // random_access.rs:409-450
+  const u32 bits = g.p0, copies = g.p1, extra = g.p2, vs = 1u << g.p0;
+  const u32 routed = (2 + vs) * copies + extra;
+  for (u32 copy = 0; copy < copies; copy++) {
+    const u32 base = (2 + vs) * copy, bbase = routed + copy * bits;
+    for (u32 i = 0; i < bits; i++) {
+      u64 b = W(bbase + i);
+      e.emit(fmul(b, fsub(b, 1)));
+    }
+    u64 acc = 0;
+    for (u32 i = bits; i-- > 0;) acc = fadd(fadd(acc, acc), W(bbase + i));
+    e.emit(fsub(acc, W(base)));
+    // fold the list: the item selected by the bits (bit 0 first, as the reference folds pairs)
+    // items at level 0 are the wires; evaluate the selection tree recursively without a buffer (bits <= 6)
+    u64 items[64];
+    for (u32 i = 0; i < vs; i++) items[i] = W(base + 2 + i);
+    u32 len = vs;
+    for (u32 i = 0; i < bits; i++) {
+      u64 b = W(bbase + i);
+      len >>= 1;
+      for (u32 k = 0; k < len; k++) items[k] = fadd(items[2 * k], fmul(b, fsub(items[2 * k + 1], items[2 * k])));
+    }
+    e.emit(fsub(items[0], W(base + 1)));
+  }
+  for (u32 i = 0; i < extra; i++) e.emit(fsub(K(i), W((2 + vs) * copies + i)));
+}
+__device__ __forceinline__ void eval_u32_arithmetic(const GateDesc& g, const u64* w, Emitter& e) {  // arithmetic_u32.rs:326-386
+  const u32 ops = g.p0;
+  for (u32 i = 0; i < ops; i++) {
+    u64 m0 = W(6 * i), m1 = W(6 * i + 1), add = W(6 * i + 2), lo = W(6 * i + 3), hi = W(6 * i + 4), inverse = W(6 * i + 5);
+    u64 computed = gl::mul_add(m0, m1, add);
+    u64 diff = fsub(0xFFFFFFFFull, hi);
+    u64 hi_not_max = fsub(fmul(inverse, diff), 1);
+    e.emit(fmul(hi_not_max, lo));
+    e.emit(fsub(fadd(fmul(hi, 1ull << 32), lo), computed));
+    u64 cl = 0, ch = 0;
+    for (u32 j = 32; j-- > 0;) {
+      u64 limb = W(6 * ops + 32 * i + j);
+      e.emit(range_product(limb, 4));
+      if (j < 16) cl = fadd(fmul(cl, 4), limb);
+      else ch = fadd(fmul(ch, 4), limb);
+    }
+    e.emit(fsub(cl, lo));
+    e.emit(fsub(ch, hi));
+  }
+}
+__device__ __forceinline__ void eval_u32_add_many(const GateDesc& g, const u64* w, Emitter& e) {  // add_many_u32.rs:143-184
+  const u32 na = g.p0, ops = g.p1;
+  for (u32 i = 0; i < ops; i++) {
+    const u32 b = (na + 3) * i;
+    u64 computed = 0;
+    for (u32 j = 0; j < na; j++) computed = fadd(computed, W(b + j));
+    computed = fadd(computed, W(b + na));
+    u64 res = W(b + na + 1), oc = W(b + na + 2);
+    e.emit(fsub(fadd(fmul(oc, 1ull << 32), res), computed));
+    u64 cr = 0, cc = 0;
+    for (u32 j = 18; j-- > 0;) {
+      u64 limb = W((na + 3) * ops + 18 * i + j);
+      e.emit(range_product(limb, 4));
+      if (j < 16) cr = fadd(fmul(cr, 4), limb);
+      else cc = fadd(fmul(cc, 4), limb);
+    }
+    e.emit(fsub(cr, res));
+    e.emit(fsub(cc, oc));
+  }
+}
+__device__ __forceinline__ void eval_u32_range_check(const GateDesc& g, const u64* w, Emitter& e) {  // range_check_u32.rs:89-111
+  const u32 n = g.p0;
+  for (u32 i = 0; i < n; i++) {
+    u64 sum = 0;
+    for (u32 j = 16; j-- > 0;) sum = fadd(fmul(sum, 4), W(n + 16 * i + j));
+    e.emit(fsub(sum, W(i)));
+    for (u32 j = 0; j < 16; j++) e.emit(range_product(W(n + 16 * i + j), 4));
+  }
+}
+__device__ __forceinline__ void eval_u32_subtraction(const GateDesc& g, const u64* w, Emitter& e) {  // subtraction_u32.rs:233-271
+  const u32 ops = g.p0;
+  for (u32 i = 0; i < ops; i++) {
+    u64 x = W(5 * i), y = W(5 * i + 1), br = W(5 * i + 2), res = W(5 * i + 3), ob = W(5 * i + 4);
+    u64 initial = fsub(fsub(x, y), br);
+    e.emit(fsub(res, fadd(initial, fmul(ob, 1ull << 32))));
+    u64 comb = 0;
+    for (u32 j = 16; j-- > 0;) {
+      u64 limb = W(5 * ops + 16 * i + j);
+      e.emit(range_product(limb, 4));
+      comb = fadd(fmul(comb, 4), limb);
+    }
+    e.emit(fsub(comb, res));
+    e.emit(fmul(ob, fsub(1, ob)));
+  }
+}
+__device__ __forceinline__ void eval_comparison(const GateDesc& g, const u64* w, Emitter& e) {  // comparison.rs:325-402
+  const u32 nc = g.p1, cb = (g.p0 + g.p1 - 1) / g.p1;
+  u64 fcomb = 0, scomb = 0;
+  for (u32 i = nc; i-- > 0;) {
+    fcomb = fadd(fmul(fcomb, 1ull << cb), W(4 + i));
+    scomb = fadd(fmul(scomb, 1ull << cb), W(4 + nc + i));
+  }
+  e.emit(fsub(fcomb, W(0)));
+  e.emit(fsub(scomb, W(1)));
+  u64 msd = 0;
+  for (u32 i = 0; i < nc; i++) {
+    u64 f = W(4 + i), s = W(4 + nc + i);
+    e.emit(range_product(f, 1u << cb));
+    e.emit(range_product(s, 1u << cb));
+    u64 diff = fsub(s, f);
+    u64 dummy = W(4 + 2 * nc + i), eq = W(4 + 3 * nc + i), inter = W(4 + 4 * nc + i);
+    e.emit(fsub(fmul(diff, dummy), fsub(1, eq)));
+    e.emit(fmul(eq, diff));
+    e.emit(fsub(inter, fmul(eq, msd)));
+    msd = fadd(inter, fmul(fsub(1, eq), diff));
+  }
+  e.emit(fsub(W(3), msd));
+  u64 bits_comb = 0;
+  for (u32 i = 0; i <= cb; i++) {
+    u64 b = W(4 + 5 * nc + i);
+    e.emit(fmul(b, fsub(1, b)));
+  }
+  for (u32 i = cb + 1; i-- > 0;) bits_comb = fadd(fadd(bits_comb, bits_comb), W(4 + 5 * nc + i));
+  e.emit(fsub(fadd(W(3), 1ull << cb), bits_comb));
+  e.emit(fsub(W(2), W(4 + 5 * nc + cb)));
+}
+// gates/poseidon.rs:485-564
+__device__ __forceinline__ void eval_poseidon(const u64* w, Emitter& e) {
+  constexpr u32 SWAP = 24, DELTA = 25, FULL0 = 29, PARTIAL = 29 + 36, FULL1 = 29 + 36 + 22;
+  u64 swap = W(SWAP);
+  e.emit(fmul(swap, fsub(swap, 1)));
+  u64 s[12];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    u64 lhs = W(i), rhs = W(i + 4), d = W(DELTA + i);
+    e.emit(fsub(fmul(swap, fsub(rhs, lhs)), d));
+    s[i] = fadd(lhs, d);
+    s[i + 4] = fsub(rhs, d);
+  }
+#pragma unroll
+  for (int i = 8; i < 12; i++) s[i] = W(i);
+  using namespace poseidon;
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = gl::add_canonical(s[i], C.rc[i]);
+#pragma unroll 1
+  for (int r = 0; r < 4; r++) {
+    if (r != 0) {
+      // state (constants of this round already folded in by the previous MDS) must equal the S-box input wires
+#pragma unroll 1
+      for (int g4 = 0; g4 < 3; g4++) {
+        // processed through the same 3 x 4 rotation as sbox_layer to keep the register array statically indexed
+        u64 t0 = s[0], t1 = s[1], t2 = s[2], t3 = s[3];
+        u64 v0 = W(FULL0 + 12 * (r - 1) + 4 * g4 + 0), v1 = W(FULL0 + 12 * (r - 1) + 4 * g4 + 1);
+        u64 v2 = W(FULL0 + 12 * (r - 1) + 4 * g4 + 2), v3 = W(FULL0 + 12 * (r - 1) + 4 * g4 + 3);
+        e.emit(fsub(t0, v0));
+        e.emit(fsub(t1, v1));
+        e.emit(fsub(t2, v2));
+        e.emit(fsub(t3, v3));
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[i] = s[i + 4];
+        s[8] = v0; s[9] = v1; s[10] = v2; s[11] = v3;
+      }
+    }
+    sbox_layer(s);
+    mds_layer(s, &C.post[12 * r]);  // + constants of the next full round / first partial constants after r = 3
+  }
+  partial_layer_init(s);
+#pragma unroll 1
+  for (int r = 0; r < 22; r++) {
+    u64 sbox_in = W(PARTIAL + r);
+    e.emit(fsub(s[0], sbox_in));
+    u64 s0 = gl::add_canonical(sbox(sbox_in), C.partial_rc[r]);  // partial_rc[21] == 0 (poseidon.rs:544 adds nothing)
+    partial_layer_fast(s, s0, r);
+  }
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = gl::add_canonical(s[i], C.rc[12 * 26 + i]);
+#pragma unroll 1
+  for (int r = 0; r < 4; r++) {
+#pragma unroll 1
+    for (int g4 = 0; g4 < 3; g4++) {
+      u64 t0 = s[0], t1 = s[1], t2 = s[2], t3 = s[3];
+      u64 v0 = W(FULL1 + 12 * r + 4 * g4 + 0), v1 = W(FULL1 + 12 * r + 4 * g4 + 1);
+      u64 v2 = W(FULL1 + 12 * r + 4 * g4 + 2), v3 = W(FULL1 + 12 * r + 4 * g4 + 3);
+      e.emit(fsub(t0, v0));
+      e.emit(fsub(t1, v1));
+      e.emit(fsub(t2, v2));
+      e.emit(fsub(t3, v3));
+#pragma unroll
+      for (int i = 0; i < 8; i++) s[i] = s[i + 4];
+      s[8] = v0; s[9] = v1; s[10] = v2; s[11] = v3;
+    }
+    sbox_layer(s);
+    mds_layer(s, &C.post[12 * (4 + r)]);
+  }
+#pragma unroll 1
+  for (int g4 = 0; g4 < 3; g4++) {
+    e.emit(fsub(s[0], W(12 + 4 * g4 + 0)));
+    e.emit(fsub(s[1], W(12 + 4 * g4 + 1)));
+    e.emit(fsub(s[2], W(12 + 4 * g4 + 2)));
+    e.emit(fsub(s[3], W(12 + 4 * g4 + 3)));
+    u64 t0 = s[0], t1 = s[1], t2 = s[2], t3 = s[3];
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = s[i + 4];
+    s[8] = t0; s[9] = t1; s[10] = t2; s[11] = t3;
+  }
+}
+#undef W
+#undef K
+
+// field inverse by Fermat (the reference uses a binary GCD, field/src/inversion.rs; the value is the same)
+__device__ __forceinline__ u64 finv(u64 a) { return gl::pow(a, gl::P - 2); }
+
+__global__ void __launch_bounds__(128) quotient_values_kernel(Params p) {
+  const u64 lde_size = (u64)1 << (p.degree_bits + p.qdb);
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= lde_size) return;
+  const u32 lde_bits = p.degree_bits + p.rate_bits;
+  const u32 step_log = p.rate_bits - p.qdb;
+  const u64 row = lde_bits ? (__brevll(i << step_log) >> (64 - lde_bits)) : 0;
+  const u64 i_next = (i + ((u64)1 << p.qdb)) & (lde_size - 1);
+  const u64 row_next = lde_bits ? (__brevll(i_next << step_log) >> (64 - lde_bits)) : 0;
+  const u64* w = p.wires + row * p.wires_stride;
+  const u64* cs = p.cs + row * p.cs_stride;
+  const u64* zp = p.zs_pp + row * p.zs_stride;
+  const u64* zn = p.zs_pp + row_next * p.zs_stride;
+  const u32 nc = p.num_challenges, nr = p.num_routed, npp = p.num_partial_products, md = p.max_degree;
+  const u32 rate_mask = (1u << p.qdb) - 1;
+
+  const u64 x = gl::mul(7, gl::pow(p.w, i));  // shifted_x = coset_shift * w^i (prover.rs:907)
+  u64 acc[MAX_CHALLENGES];
+#pragma unroll
+  for (int c = 0; c < MAX_CHALLENGES; c++) acc[c] = 0;
+
+  // ---- vanishing_z_1_terms and partial-product checks (vanishing_poly.rs:160-205) ----
+  // reduce_with_powers_multi reduces ONE term list [z1 terms of every challenge | pp checks of every challenge |
+  // gate constraints] with each alpha, so the terms produced for challenge tc enter every challenge c's sum.
+  {
+    // eval_l_0 (zero_poly_coset.rs:57-60)
+    const u64 l0 = gl::mul(p.zh[i & rate_mask], finv(gl::mul(p.n_field, gl::sub(x, 1))));
+    const u32 chunks = npp + 1;
+    for (u32 tc = 0; tc < nc; tc++) {
+      const u64 z_x = __ldg(zp + tc), z_gx = __ldg(zn + tc);
+      const u64 t_z1 = gl::mul(l0, gl::sub(z_x, 1));
+      for (u32 c = 0; c < nc; c++) acc[c] = gl::mul_add(t_z1, __ldg(p.alpha_pows + (u64)c * p.num_terms + tc), acc[c]);
+      const u64 beta = p.betas[tc], gamma = p.gammas[tc];
+      const u64 bx = gl::mul(beta, x);
+      u64 prev = z_x;
+      for (u32 ch = 0; ch < chunks; ch++) {
+        u64 num = 1, den = 1;
+        const u32 j1 = min(nr, (ch + 1) * md);
+        for (u32 j = ch * md; j < j1; j++) {
+          const u64 wv = __ldg(w + j);
+          num = gl::mul(num, gl::add(gl::add(wv, gl::mul(bx, __ldg(p.k_is + j))), gamma));               // :175-181
+          den = gl::mul(den, gl::add(gl::add(wv, gl::mul(beta, __ldg(cs + p.num_constants + j))), gamma));  // :182-186
+        }
+        const u64 next = ch + 1 < chunks ? __ldg(zp + nc + tc * npp + ch) : z_gx;
+        const u64 term = gl::sub(gl::mul(prev, num), gl::mul(next, den));  // partial_products.rs:70-75
+        for (u32 c = 0; c < nc; c++)
+          acc[c] = gl::mul_add(term, __ldg(p.alpha_pows + (u64)c * p.num_terms + nc + tc * chunks + ch), acc[c]);
+        prev = next;
+      }
+    }
+  }
+
+  // ---- gate constraints (vanishing_poly.rs:267-306) ----
+  const u32 gate_base = nc * (npp + 2);
+  const u64* kc = cs + p.num_selectors;  // vars.remove_prefix(num_selectors), gate.rs:138
+  for (u32 gi = 0; gi < p.num_gates; gi++) {
+    const GateDesc g = p.gates[gi];
+    // compute_filter (gate.rs:261-268)
+    const u64 s = __ldg(cs + g.selector_index);
+    u64 filter = 1;
+    for (u32 k = g.group_start; k < g.group_end; k++)
+      if (k != gi) filter = gl::mul(filter, gl::sub((u64)k, s));
+    if (p.num_selectors > 1) filter = gl::mul(filter, gl::sub(0xFFFFFFFFull, s));
+    Emitter e;
+    e.init(p.alpha_pows, p.num_terms, gate_base, nc);
+    switch (g.type) {
+      case G_NOOP: break;
+      case G_CONSTANT: eval_constant(g, w, kc, e); break;
+      case G_PUBLIC_INPUT: eval_public_input(w, p.pih, e); break;
+      case G_ARITHMETIC: eval_arithmetic(g, w, kc, e); break;
+      case G_BASE_SUM: eval_base_sum(g, w, e); break;
+      case G_POSEIDON: eval_poseidon(w, e); break;
+      case G_RANDOM_ACCESS: eval_random_access(g, w, kc, e); break;
+      case G_U32_ARITHMETIC: eval_u32_arithmetic(g, w, e); break;
+      case G_U32_ADD_MANY: eval_u32_add_many(g, w, e); break;
+      case G_U32_RANGE_CHECK: eval_u32_range_check(g, w, e); break;
+      case G_U32_SUBTRACTION: eval_u32_subtraction(g, w, e); break;
+      case G_COMPARISON: eval_comparison(g, w, e); break;
+      default: break;
+    }
+#pragma unroll
+    for (int c = 0; c < MAX_CHALLENGES; c++)
+      if ((u32)c < nc) acc[c] = gl::mul_add(filter, e.acc[c], acc[c]);
+  }
+
+  // ---- divide by Z_H (prover.rs:985-991) ----
+  const u64 zi = p.zh_inv[i & rate_mask];
+#pragma unroll
+  for (int c = 0; c < MAX_CHALLENGES; c++) {
+    if ((u32)c < nc) {
+      const u64 v = gl::canon(gl::mul(acc[c], zi));
+      p.out_values[(u64)c * lde_size + i] = v;
+      if (p.out_rows) p.out_rows[i * nc + c] = v;
+    }
+  }
+}
+
+// coefficients[i] *= shift_inv^i  (coset_ifft, field/src/polynomial/mod.rs:64-77)
+__global__ void scale_by_powers_kernel(u64* __restrict__ v, u64 len, u64 ncols, u64 base) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  u64 pw = gl::pow(base, i);
+  for (u64 c = 0; c < ncols; c++) v[c * len + i] = gl::canon(gl::mul(v[c * len + i], pw));
+}
+
+// alpha_pows[c][t] = alpha_c^t
+__global__ void alpha_pows_kernel(u64* __restrict__ out, u32 num_terms, u32 nc, const u64* __restrict__ alphas) {
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= num_terms) return;
+  for (u32 c = 0; c < nc; c++) out[(u64)c * num_terms + t] = gl::canon(gl::pow(alphas[c], t));
+}
+
+}  // namespace quotient

@@ -1,0 +1,105 @@
+"""GPU: compute_quotient_polys on the device (through the C ABI) against the Python restatement of
+plonky2/src/plonk/prover.rs:790-1034 -- bit-exact quotient evaluations and coefficients."""
+import numpy as np
+import pytest
+
+import oracle
+import plonky2_gpu_b200 as p2b
+from oracle import quotient as Q
+from tests import quotient_fixtures as F
+
+pytestmark = pytest.mark.gpu
+P = Q.P
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    p2b.build()
+    c = p2b.Context()
+    yield c
+    c.close()
+
+
+def to_p2b_circuit(circ):
+    gates = [(g.type_id, g.params) for g in circ.gates]
+    return p2b.Circuit(gates, circ.selector_indices, circ.groups, circ.num_wires, circ.num_routed_wires, circ.num_constants,
+                       circ.k_is, circ.degree_bits, circ.rate_bits, circ.num_challenges, circ.quotient_degree_factor)
+
+
+def run_both(ctx, inst, cap_height=0):
+    c = inst.circ
+    bw = p2b.PolynomialBatch.from_values(ctx, inst.wires, c.rate_bits, cap_height)
+    bz = p2b.PolynomialBatch.from_values(ctx, inst.zs_pp, c.rate_bits, cap_height)
+    bc = p2b.PolynomialBatch.from_values(ctx, inst.consts_sigmas, c.rate_bits, cap_height)
+    vals, coeffs = p2b.compute_quotient_polys(ctx, to_p2b_circuit(c), bw, bz, bc, inst.pih, inst.betas, inst.gammas, inst.alphas)
+    ow = oracle.batch_from_values(inst.wires, c.rate_bits, 0, want_digests=False).leaves
+    oz = oracle.batch_from_values(inst.zs_pp, c.rate_bits, 0, want_digests=False).leaves
+    oc = oracle.batch_from_values(inst.consts_sigmas, c.rate_bits, 0, want_digests=False).leaves
+    evals, ecoeffs = Q.compute_quotient_polys(c, ow, oz, oc, inst.pih, inst.betas, inst.gammas, inst.alphas)
+    for b in (bw, bz, bc):
+        b.close()
+    return vals, coeffs, evals, ecoeffs
+
+
+@pytest.mark.parametrize("which,degree_bits", [(0, 4), (1, 4), (1, 6)])
+def test_quotient_honest_witness_matches_oracle(ctx, which, degree_bits):
+    gates, groups, sel = F.standard_gate_sets()[which]
+    inst = F.build_instance(gates, groups, sel, degree_bits, 135, 80, seed=21 + which)
+    vals, coeffs, evals, ecoeffs = run_both(ctx, inst)
+    n = 1 << degree_bits
+    for c in range(inst.circ.num_challenges):
+        assert np.array_equal(vals[c], evals[c])
+        assert np.array_equal(coeffs[c], ecoeffs[c])
+        assert not np.any(coeffs[c][7 * n:])  # honest witness: degree < 7n (size-independent property)
+
+
+def test_quotient_random_data_matches_oracle(ctx):
+    # no constraint holds on random data: every term of the alpha reduction is exercised with non-zero values,
+    # including real partial products / Z columns and a non-identity sigma
+    gates, groups, sel = F.standard_gate_sets()[1]
+    inst = F.build_instance(gates, groups, sel, 4, 135, 80, seed=31)
+    rng = np.random.default_rng(32)
+    for m in (inst.wires, inst.zs_pp, inst.consts_sigmas):
+        m[:] = rng.integers(0, P, size=m.shape, dtype=np.uint64)
+    vals, coeffs, evals, ecoeffs = run_both(ctx, inst)
+    for c in range(inst.circ.num_challenges):
+        assert np.array_equal(vals[c], evals[c])
+        assert np.array_equal(coeffs[c], ecoeffs[c])
+
+
+@pytest.mark.parametrize("num_wires,num_routed,nch,qdf,rate_bits", [(136, 80, 2, 8, 3), (234, 80, 2, 8, 3), (40, 12, 3, 4, 2), (60, 9, 1, 8, 3)])
+def test_quotient_other_configs(ctx, num_wires, num_routed, nch, qdf, rate_bits):
+    # standard_ecc_config (136 wires), wide_ecc_config (234 wires) and odd shapes (routed wires not a multiple of the
+    # chunk size, 1 and 3 challenges, quotient degree factor 4)
+    gates = [Q.NoopGate(), Q.ConstantGate(2), Q.PublicInputGate(), Q.ArithmeticGate(num_routed // 4),
+             Q.U32SubtractionGate(Q.U32SubtractionGate.num_ops_for(num_wires, num_routed)), Q.ComparisonGate(6, 3)]
+    groups, sel = [(0, 3), (3, 6)], [0, 0, 0, 1, 1, 1]
+    inst = F.build_instance(gates, groups, sel, 4, num_wires, num_routed, seed=41, rate_bits=rate_bits, num_challenges=nch,
+                            quotient_degree_factor=qdf)
+    rng = np.random.default_rng(42)
+    inst.zs_pp[:] = rng.integers(0, P, size=inst.zs_pp.shape, dtype=np.uint64)
+    vals, coeffs, evals, ecoeffs = run_both(ctx, inst)
+    for c in range(nch):
+        assert np.array_equal(vals[c], evals[c])
+        assert np.array_equal(coeffs[c], ecoeffs[c])
+
+
+def test_quotient_error_paths(ctx):
+    gates, groups, sel = F.standard_gate_sets()[0]
+    inst = F.build_instance(gates, groups, sel, 3, 135, 80, seed=51)
+    c = inst.circ
+    bw = p2b.PolynomialBatch.from_values(ctx, inst.wires, 3, 0)
+    bz = p2b.PolynomialBatch.from_values(ctx, inst.zs_pp, 3, 0)
+    bc = p2b.PolynomialBatch.from_values(ctx, inst.consts_sigmas, 3, 0)
+    bad = p2b.Circuit([(99, ())], [0], [(0, 1)], 135, 80, c.num_constants, c.k_is, 3)
+    with pytest.raises(p2b.P2BError, match="unknown gate type"):
+        p2b.compute_quotient_polys(ctx, bad, bw, bz, bc, inst.pih, inst.betas, inst.gammas, inst.alphas)
+    wrong_deg = p2b.Circuit([(0, ())], [0], [(0, 1)], 135, 80, c.num_constants, c.k_is, 5)
+    with pytest.raises(p2b.P2BError, match="batch shape"):
+        p2b.compute_quotient_polys(ctx, wrong_deg, bw, bz, bc, inst.pih, inst.betas, inst.gammas, inst.alphas)
+    # quotient degree factor above the rate is refused like prover.rs:809-813
+    high = p2b.Circuit([(0, ())], [0], [(0, 1)], 135, 80, c.num_constants, c.k_is, 3, rate_bits=3, quotient_degree_factor=16)
+    with pytest.raises(p2b.P2BError, match="higher than the rate"):
+        p2b.compute_quotient_polys(ctx, high, bw, bz, bc, inst.pih, inst.betas, inst.gammas, inst.alphas)
+    for b in (bw, bz, bc):
+        b.close()
