@@ -249,7 +249,19 @@ p2b_rust_error merkle_tree_from_coeffs(uint64_t* d_values_flatten, uint64_t* d_e
                                        void* ctx); /* lib.rs:100-114 */
 p2b_rust_error transpose(uint64_t* d_ext_values_flatten, int poly_num, int values_num_per_poly, int rate_bits,
                          int salt_size, int pad_extvalues_len, void* ctx); /* plonky2_gpu.cu:192-215 */
+/* lib.rs:117-143.  The reference kernel is compiled for ONE circuit; this one evaluates the circuit registered with
+ * p2b_compat_set_circuit().  d_outs: [N][num_challenges] values, d_quotient_polys: [num_challenges][N] coefficients. */
+p2b_rust_error compute_quotient_polys(const uint64_t* d_ext_values_flatten, int poly_num, int values_num_per_poly, int log_len,
+                                      const uint64_t* d_root_table2, const uint64_t* d_shift_inv_powers, int rate_bits,
+                                      int salt_size, const p2b_data_slice* zs_partial_products_commitment_leaves,
+                                      const p2b_data_slice* constants_sigmas_commitment_leaves, void* d_outs,
+                                      void* d_quotient_polys, const p2b_data_slice* points,
+                                      const p2b_data_slice* z_h_on_coset_evals, const p2b_data_slice* z_h_on_coset_inverses,
+                                      const p2b_data_slice* k_is, const p2b_data_slice* alphas, const p2b_data_slice* betas,
+                                      const p2b_data_slice* gammas, void* ctx);
 #endif
+/* Registers the circuit (and the public-inputs hash) the legacy compute_quotient_polys symbol evaluates. */
+int p2b_compat_set_circuit(const p2b_circuit* circuit, const uint64_t* public_inputs_hash /* host [4] */);
 
 #ifdef __cplusplus
 }

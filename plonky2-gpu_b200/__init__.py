@@ -47,6 +47,11 @@ class BatchInfo(C.Structure):
                 ("leaf_len", C.c_uint64), ("num_digests", C.c_uint64)]
 
 
+class DataSlice(C.Structure):
+    """DataSlice (cuda/src/lib.rs:52-56)"""
+    _fields_ = [("ptr", C.c_void_p), ("len", C.c_int)]
+
+
 class Gate(C.Structure):
     """p2b_gate (include/plonky2_b200.h): one entry of common_data.gates with its selector group."""
     _fields_ = [("type", C.c_uint32), ("selector_index", C.c_uint32), ("group_start", C.c_uint32), ("group_end", C.c_uint32),
@@ -152,6 +157,8 @@ def lib():
         "merkle_tree_from_values": (RustError, [vp, vp, i, i, i, vp, vp, vp, vp, i, i, i, i, vp]),
         "merkle_tree_from_coeffs": (RustError, [vp, vp, i, i, i, vp, vp, vp, i, i, i, i, vp]),
         "transpose": (RustError, [vp, i, i, i, i, i, vp]),
+        "compute_quotient_polys": (RustError, [vp, i, i, i, vp, vp, i, i, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "p2b_compat_set_circuit": (i, [C.POINTER(CircuitStruct), vp]),
     }
     for name, (res, args) in sigs.items():
         f = getattr(L, name)

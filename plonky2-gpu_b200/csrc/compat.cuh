@@ -207,3 +207,83 @@ extern "C" p2b_rust_error transpose(uint64_t* d_ext_values_flatten, int poly_num
   c->stream = saved;
   return rc == P2B_OK ? rust_ok() : rust_err(rc);
 }
+
+// compute_quotient_polys (lib.rs:117-143; plonky2_gpu.cu:609-783).  The reference's kernel is compiled for one circuit
+// (literal gate list, constraint count and public-input hash, plonky2_gpu.cu:665-689, plonky2_gpu_impl.cuh:600-685), so its
+// C signature carries no circuit description.  Here the host registers the circuit once with p2b_compat_set_circuit()
+// (the data CommonCircuitData already holds) and the legacy symbol evaluates THAT circuit:
+//   d_ext_values_flatten : wires leaves (leaf-major, leaf_len = poly_num + salt_size)
+//   zs_partial_products_commitment_leaves / constants_sigmas_commitment_leaves : device rows, len = N * leaf_len
+//   d_outs : [N][num_challenges] quotient values (the reference's point-major layout, plonky2_gpu_impl.cuh:874-875)
+//   d_quotient_polys : [num_challenges][N] coefficients after iNTT and the g^-i scaling (plonky2_gpu.cu:735-760)
+//   alphas / betas / gammas / k_is : DEVICE slices, as the Rust side uploads them (prover.rs:429-533)
+//   points / z_h_on_coset_* / root_table2 / shift_inv_powers : accepted and ignored (recomputed by the library)
+struct CompatCircuit {
+  bool set = false;
+  p2b_circuit circ{};
+  std::vector<p2b_gate> gates;
+  std::vector<u64> k_is;
+  u64 pih[4] = {0, 0, 0, 0};
+};
+static CompatCircuit g_compat_circuit;
+
+extern "C" int p2b_compat_set_circuit(const p2b_circuit* circuit, const uint64_t* public_inputs_hash) {
+  if (!circuit || !public_inputs_hash) return fail(P2B_ERR_INVALID, "NULL argument");
+  std::lock_guard<std::mutex> lk(g_compat_mu);
+  CompatCircuit& cc = g_compat_circuit;
+  cc.circ = *circuit;
+  cc.gates.assign(circuit->gates, circuit->gates + circuit->num_gates);
+  cc.k_is.assign(circuit->k_is, circuit->k_is + circuit->num_routed_wires);
+  cc.circ.gates = cc.gates.data();
+  cc.circ.k_is = cc.k_is.data();
+  for (int i = 0; i < 4; i++) cc.pih[i] = public_inputs_hash[i];
+  cc.set = true;
+  return P2B_OK;
+}
+
+extern "C" p2b_rust_error compute_quotient_polys(const uint64_t* d_ext_values_flatten, int poly_num, int values_num_per_poly,
+                                                 int log_len, const uint64_t* d_root_table2, const uint64_t* d_shift_inv_powers,
+                                                 int rate_bits, int salt_size, const p2b_data_slice* zs_pp_leaves,
+                                                 const p2b_data_slice* consts_sigmas_leaves, void* d_outs, void* d_quotient_polys,
+                                                 const p2b_data_slice* points, const p2b_data_slice* z_h_on_coset_evals,
+                                                 const p2b_data_slice* z_h_on_coset_inverses, const p2b_data_slice* k_is,
+                                                 const p2b_data_slice* alphas, const p2b_data_slice* betas,
+                                                 const p2b_data_slice* gammas, void* ctx) {
+  (void)d_root_table2; (void)d_shift_inv_powers; (void)points; (void)z_h_on_coset_evals; (void)z_h_on_coset_inverses; (void)k_is;
+  CompatCircuit& cc = g_compat_circuit;
+  if (!cc.set) {
+    fail(P2B_ERR_INVALID, "compute_quotient_polys: no circuit registered; call p2b_compat_set_circuit() first (the reference kernel "
+                          "hard-codes its circuit, this library takes it as data)");
+    return rust_err(P2B_ERR_INVALID);
+  }
+  const p2b_circuit& circ = cc.circ;
+  if (!d_ext_values_flatten || !zs_pp_leaves || !consts_sigmas_leaves || !d_quotient_polys || !alphas || !betas || !gammas ||
+      log_len != (int)circ.degree_bits || rate_bits != (int)circ.rate_bits || values_num_per_poly != (1 << log_len) ||
+      poly_num < (int)circ.num_wires || alphas->len != (int)circ.num_challenges || betas->len != (int)circ.num_challenges ||
+      gammas->len != (int)circ.num_challenges) {
+    fail(P2B_ERR_INVALID, "compute_quotient_polys: arguments do not match the registered circuit");
+    return rust_err(P2B_ERR_INVALID);
+  }
+  const u64 N = (u64)values_num_per_poly << rate_bits;
+  if (zs_pp_leaves->len <= 0 || consts_sigmas_leaves->len <= 0 || (u64)zs_pp_leaves->len % N || (u64)consts_sigmas_leaves->len % N) {
+    fail(P2B_ERR_INVALID, "compute_quotient_polys: leaf slices are not a multiple of the LDE size");
+    return rust_err(P2B_ERR_INVALID);
+  }
+  p2b_ctx* c;
+  cudaStream_t saved;
+  int rc = compat_ctx(ctx, &c, &saved);
+  if (rc != P2B_OK) return rust_err(rc);
+  u64 h[3][quotient::MAX_CHALLENGES];
+  const p2b_data_slice* sl[3] = {alphas, betas, gammas};
+  for (int k = 0; k < 3 && rc == P2B_OK; k++)
+    if (cudaMemcpyAsync(h[k], sl[k]->ptr, circ.num_challenges * sizeof(u64), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess)
+      rc = fail(P2B_ERR_CUDA, "copy of challenges failed");
+  if (rc == P2B_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(P2B_ERR_CUDA, "stream synchronize failed");
+  if (rc == P2B_OK)
+    rc = quotient_impl(c, &circ, d_ext_values_flatten, (u64)poly_num + salt_size, (const u64*)zs_pp_leaves->ptr,
+                       (u64)zs_pp_leaves->len / N, (const u64*)consts_sigmas_leaves->ptr, (u64)consts_sigmas_leaves->len / N, cc.pih,
+                       h[1], h[2], h[0], nullptr, (u64*)d_quotient_polys, (u64*)d_outs);
+  if (rc == P2B_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(P2B_ERR_CUDA, "stream synchronize failed");
+  c->stream = saved;
+  return rc == P2B_OK ? rust_ok() : rust_err(rc);
+}

@@ -26,7 +26,7 @@ def declared_symbols():
 def test_header_declares_the_reference_ffi_symbols():
     syms = declared_symbols()
     # cuda/src/lib.rs:52-145
-    for ref in ["init", "ifft", "build_merkle_tree", "merkle_tree_from_values", "merkle_tree_from_coeffs"]:
+    for ref in ["init", "ifft", "build_merkle_tree", "merkle_tree_from_values", "merkle_tree_from_coeffs", "compute_quotient_polys"]:
         assert ref in syms, ref
     assert len([s for s in syms if s.startswith("p2b_")]) >= 30
 

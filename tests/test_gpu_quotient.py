@@ -103,3 +103,47 @@ def test_quotient_error_paths(ctx):
         p2b.compute_quotient_polys(ctx, high, bw, bz, bc, inst.pih, inst.betas, inst.gammas, inst.alphas)
     for b in (bw, bz, bc):
         b.close()
+
+
+def test_legacy_compute_quotient_polys_symbol(ctx):
+    """The reference's own symbol (cuda/src/lib.rs:117-143) with device slices, on a registered circuit."""
+    import ctypes as C
+    gates, groups, sel = F.standard_gate_sets()[1]
+    inst = F.build_instance(gates, groups, sel, 4, 135, 80, seed=61)
+    c = inst.circ
+    rng = np.random.default_rng(62)
+    inst.zs_pp[:] = rng.integers(0, P, size=inst.zs_pp.shape, dtype=np.uint64)
+    bw = p2b.PolynomialBatch.from_values(ctx, inst.wires, 3, 4)
+    bz = p2b.PolynomialBatch.from_values(ctx, inst.zs_pp, 3, 4)
+    bc = p2b.PolynomialBatch.from_values(ctx, inst.consts_sigmas, 3, 4)
+    pc = to_p2b_circuit(c)
+    L = p2b.lib()
+    p2b._check(L.p2b_compat_set_circuit(C.byref(pc.struct), (C.c_uint64 * 4)(*inst.pih)))
+    N = 1 << (4 + 3)
+    dev = lambda xs: p2b.DeviceBuffer.from_host(ctx, np.array(xs, dtype=np.uint64))
+    da, db, dg, dk = dev(inst.alphas), dev(inst.betas), dev(inst.gammas), dev(c.k_is)
+    d_outs, d_q = p2b.DeviceBuffer(ctx, 2 * N), p2b.DeviceBuffer(ctx, 2 * N)
+    sl = lambda ptr, ln: C.byref(p2b.DataSlice(ptr, ln))
+    import torch
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    class RefStreams(C.Structure):
+        _fields_ = [("stream", C.c_void_p), ("stream2", C.c_void_p)]
+    streams = RefStreams(s1.cuda_stream, s2.cuda_stream)
+    pw, pz, pcs = bw.device_ptrs()["leaves"], bz.device_ptrs()["leaves"], bc.device_ptrs()["leaves"]
+    ctx.synchronize()
+    e = L.compute_quotient_polys(pw, 135, 16, 4, None, None, 3, 0, sl(pz, N * bz.leaf_len), sl(pcs, N * bc.leaf_len), d_outs.ptr, d_q.ptr,
+                                 sl(None, N), sl(None, 8), sl(None, 8), sl(dk.ptr, 80), sl(da.ptr, 2), sl(db.ptr, 2), sl(dg.ptr, 2),
+                                 C.byref(streams))
+    assert e.code == 0
+    ow = oracle.batch_from_values(inst.wires, 3, 0, want_digests=False).leaves
+    oz = oracle.batch_from_values(inst.zs_pp, 3, 0, want_digests=False).leaves
+    oc = oracle.batch_from_values(inst.consts_sigmas, 3, 0, want_digests=False).leaves
+    evals, ecoeffs = Q.compute_quotient_polys(c, ow, oz, oc, inst.pih, inst.betas, inst.gammas, inst.alphas)
+    outs = d_outs.to_host().reshape(N, 2)
+    polys = d_q.to_host().reshape(2, N)
+    for ch in range(2):
+        assert np.array_equal(outs[:, ch], evals[ch])
+        assert np.array_equal(polys[ch], ecoeffs[ch])
+    for b in (bw, bz, bc):
+        b.close()
