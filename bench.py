@@ -259,10 +259,11 @@ def run_b200(args, rank, world, local_rank):
 
     def step_e2e():
         if world == 1:
-            b = p2b.PolynomialBatch.from_values(ctx, hv[:P], RATE_BITS, CAP_HEIGHT)   # H2D inside
-            b.cap(out=cap_host)                                                       # D2H result
-            b.polynomials(out=hc[:P])                                                 # D2H coefficients (the reference
-            b.close()                                                                 # keeps them host-side, oracle.rs:403-407)
+            # H2D of the values and D2H of the coefficients (the reference keeps them host-side, oracle.rs:403-407)
+            # happen inside the call, overlapped with the transforms / the tree
+            b = p2b.PolynomialBatch.from_values(ctx, hv[:P], RATE_BITS, CAP_HEIGHT, coeffs_out=hc[:P])
+            b.cap(out=cap_host)                                                       # D2H result (synchronises)
+            b.close()
         else:
             p2b._check(L.p2b_memcpy_h2d(ctx.handle, work.data_ptr(), host_vals.ptr, (c1 - c0) * n * 8))
             b = sharded.sharded_commit_from_values(engine, comm, work, P, n_log, RATE_BITS, CAP_HEIGHT)

@@ -86,6 +86,14 @@ int p2b_commit_from_values(p2b_ctx* ctx, const uint64_t* values, int values_on_h
 int p2b_commit_from_coeffs(p2b_ctx* ctx, const uint64_t* coeffs, int coeffs_on_host, uint32_t n_log, uint64_t P,
                            uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, int salt_on_host,
                            p2b_batch** out);
+/* from_values with the host-side data movement of the reference's caller folded in (fri/oracle.rs:352-362, 403-407):
+ * host values are uploaded in column groups while earlier groups are already being transformed, and, if
+ * coeffs_host_out (pinned host memory, [P][n]) is given, the coefficients are copied back on the D2H engine while the
+ * LDE and the Merkle tree are computed.  The copy is complete once the context stream has been synchronised
+ * (p2b_ctx_synchronize, or any p2b_batch_get_*). */
+int p2b_commit_from_values_ex(p2b_ctx* ctx, const uint64_t* values, int values_on_host, uint32_t n_log, uint64_t P,
+                              uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, int salt_on_host,
+                              uint64_t* coeffs_host_out, p2b_batch** out);
 void p2b_batch_destroy(p2b_batch* b);
 
 typedef struct {

@@ -119,6 +119,7 @@ def lib():
         "p2b_ctx_leaf_hash_time": (i, [vp, C.POINTER(C.c_double), C.POINTER(u64)]),
         "p2b_commit_from_values": (i, [vp, vp, i, u32, u64, u32, u32, vp, i, C.POINTER(vp)]),
         "p2b_commit_from_coeffs": (i, [vp, vp, i, u32, u64, u32, u32, vp, i, C.POINTER(vp)]),
+        "p2b_commit_from_values_ex": (i, [vp, vp, i, u32, u64, u32, u32, vp, i, vp, C.POINTER(vp)]),
         "p2b_batch_destroy": (None, [vp]),
         "p2b_batch_get_info": (i, [vp, C.POINTER(BatchInfo)]),
         "p2b_batch_device_ptrs": (i, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
@@ -393,8 +394,13 @@ class PolynomialBatch:
         return PolynomialBatch(ctx, h.value)
 
     @classmethod
-    def from_values(cls, ctx, values, rate_bits, cap_height, blinding=False, salt=None):
-        """fri/oracle.rs:709-731.  values: [P][n] numpy array (host) or (DeviceBuffer, P, n)."""
+    def from_values(cls, ctx, values, rate_bits, cap_height, blinding=False, salt=None, coeffs_out=None):
+        """fri/oracle.rs:709-731.  values: [P][n] numpy array (host) or (DeviceBuffer, P, n).
+        coeffs_out: optional pinned host array [P][n] that receives the coefficients while the tree is built."""
+        if coeffs_out is not None:
+            ptr = coeffs_out.ctypes.data
+            fn = lambda *a: lib().p2b_commit_from_values_ex(*a[:-1], ptr, a[-1])
+            return cls._commit(fn, ctx, values, rate_bits, cap_height, salt, blinding)
         return cls._commit(lib().p2b_commit_from_values, ctx, values, rate_bits, cap_height, salt, blinding)
 
     @classmethod

@@ -95,6 +95,8 @@ struct p2b_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;   // NTT passes, tree layers, copies
   cudaStream_t stream2 = nullptr;  // leaf hashing of block b overlaps the NTT of block b+1
+  cudaStream_t stream_h2d = nullptr, stream_d2h = nullptr;  // host copies overlapped with compute (one DMA engine each way)
+  cudaEvent_t ev_copy[32] = {};
   bool owns_streams = true;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   std::vector<cudaEvent_t> ev_pool;
@@ -180,6 +182,7 @@ static int ctx_init_common(p2b_ctx* c) {
   CUDA_TRY(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreate(&c->ev_t0));
   CUDA_TRY(cudaEventCreate(&c->ev_t1));
+  for (auto& e : c->ev_copy) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CUDA_TRY(poseidon::upload_constants());
   // let the stream-ordered pool keep its memory between commits (no OS round trip inside a timed step)
   cudaMemPool_t pool;
@@ -204,7 +207,9 @@ extern "C" int p2b_ctx_create(int device, p2b_ctx** out) {
   int rc = P2B_OK;
   cudaError_t e;
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
-      (e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking)) != cudaSuccess)
+      (e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&c->stream_h2d, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&c->stream_d2h, cudaStreamNonBlocking)) != cudaSuccess)
     rc = fail(P2B_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
   if (rc == P2B_OK) rc = ctx_init_common(c);
   if (rc != P2B_OK) {
@@ -230,6 +235,10 @@ extern "C" void p2b_ctx_destroy(p2b_ctx* c) {
     cudaEventDestroy(pr.first);
     cudaEventDestroy(pr.second);
   }
+  for (cudaEvent_t e : c->ev_copy)
+    if (e) cudaEventDestroy(e);
+  if (c->stream_h2d) cudaStreamDestroy(c->stream_h2d);
+  if (c->stream_d2h) cudaStreamDestroy(c->stream_d2h);
   if (c->owns_streams) {
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->stream2) cudaStreamDestroy(c->stream2);
@@ -242,6 +251,8 @@ extern "C" int p2b_ctx_synchronize(p2b_ctx* c) {
   if (!c) return fail(P2B_ERR_INVALID, "ctx is NULL");
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream2));
+  CUDA_TRY(cudaStreamSynchronize(c->stream_h2d));
+  CUDA_TRY(cudaStreamSynchronize(c->stream_d2h));
   return P2B_OK;
 }
 extern "C" uint64_t p2b_ctx_launch_count(const p2b_ctx* c) { return c ? c->launches : 0; }
@@ -535,7 +546,7 @@ static int lde_and_merkle(p2b_ctx* c, const u64* coeffs_d, u32 k, u64 P, u32 rat
 
 static int commit_impl(p2b_ctx* c, const u64* input, int on_host, bool is_values, u32 k, u64 P, u32 rate_bits,
                        u32 cap_height, const u64* salt, int salt_on_host, p2b_batch** out, u64 block_first = 0,
-                       u64 block_count = ~(u64)0) {
+                       u64 block_count = ~(u64)0, u64* coeffs_host_out = nullptr) {
   if (!c || !out) return fail(P2B_ERR_INVALID, "NULL argument");
   *out = nullptr;
   if (!input || P == 0) return fail(P2B_ERR_INVALID, "empty batch (no polynomials)");
@@ -572,7 +583,24 @@ static int commit_impl(p2b_ctx* c, const u64* input, int on_host, bool is_values
     CUDA_TRY(cudaMallocAsync(&b->cap, ncap * 4 * sizeof(u64), st));
     P2B_TRY(ensure_scratch(c, P * n));
     const u64* in_d = input;
-    if (on_host) {
+    bool ifft_done = false;
+    if (on_host && is_values && P >= 16) {
+      // Host values: H2D in column groups on the copy stream, each group's inverse NTT starts as soon as its columns
+      // have landed (the transform is per column), so only the last group's transform is exposed after the copy.
+      const u32 groups = 16;
+      CUDA_TRY(cudaEventRecord(c->ev_copy[31], st));                 // allocations above are stream-ordered on st
+      CUDA_TRY(cudaStreamWaitEvent(c->stream_h2d, c->ev_copy[31], 0));
+      for (u32 g = 0; g < groups; g++) {
+        u64 c0 = P * g / groups, c1 = P * (g + 1) / groups;
+        if (c1 == c0) continue;
+        CUDA_TRY(cudaMemcpyAsync(b->coeffs + c0 * n, input + c0 * n, (c1 - c0) * n * sizeof(u64), cudaMemcpyHostToDevice, c->stream_h2d));
+        CUDA_TRY(cudaEventRecord(c->ev_copy[g], c->stream_h2d));
+        CUDA_TRY(cudaStreamWaitEvent(st, c->ev_copy[g], 0));
+        P2B_TRY(run_ifft(c, b->coeffs + c0 * n, b->coeffs + c0 * n, c->scratch + c0 * n, k, c1 - c0));
+      }
+      in_d = b->coeffs;
+      ifft_done = true;
+    } else if (on_host) {
       // host input goes straight into the coefficient buffer (values are transformed in place there)
       CUDA_TRY(cudaMemcpyAsync(b->coeffs, input, P * n * sizeof(u64), cudaMemcpyHostToDevice, st));
       in_d = b->coeffs;
@@ -586,12 +614,22 @@ static int commit_impl(p2b_ctx* c, const u64* input, int on_host, bool is_values
       }
     }
     if (is_values) {
-      P2B_TRY(run_ifft(c, in_d, b->coeffs, c->scratch, k, P));
+      if (!ifft_done) P2B_TRY(run_ifft(c, in_d, b->coeffs, c->scratch, k, P));
     } else if (!on_host) {
       CUDA_TRY(cudaMemcpyAsync(b->coeffs, input, P * n * sizeof(u64), cudaMemcpyDeviceToDevice, st));
     }
+    if (coeffs_host_out) {
+      // coefficients back to the host (the reference keeps `polynomials` host-side, oracle.rs:403-407) on the D2H
+      // engine while the LDE and the Merkle tree are computed
+      CUDA_TRY(cudaEventRecord(c->ev_copy[30], st));
+      CUDA_TRY(cudaStreamWaitEvent(c->stream_d2h, c->ev_copy[30], 0));
+      CUDA_TRY(cudaMemcpyAsync(coeffs_host_out, b->coeffs, P * n * sizeof(u64), cudaMemcpyDeviceToHost, c->stream_d2h));
+      CUDA_TRY(cudaEventRecord(c->ev_copy[29], c->stream_d2h));
+    }
     P2B_TRY(lde_and_merkle(c, b->coeffs, k, P, rate_bits, cap_height, salt_d, c->scratch, b->leaves, leaf_len,
                            b->digests, b->cap, false, nullptr, block_first, block_count, &b->top_layer));
+    // a later synchronisation of the main stream also covers the coefficient copy
+    if (coeffs_host_out) CUDA_TRY(cudaStreamWaitEvent(st, c->ev_copy[29], 0));
     return P2B_OK;
   };
   rc = body();
@@ -609,6 +647,12 @@ extern "C" int p2b_commit_from_values(p2b_ctx* ctx, const uint64_t* values, int 
                                       uint64_t P, uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt,
                                       int salt_on_host, p2b_batch** out) {
   return commit_impl(ctx, values, values_on_host, true, n_log, P, rate_bits, cap_height, salt, salt_on_host, out);
+}
+extern "C" int p2b_commit_from_values_ex(p2b_ctx* ctx, const uint64_t* values, int values_on_host, uint32_t n_log, uint64_t P,
+                                         uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt, int salt_on_host,
+                                         uint64_t* coeffs_host_out, p2b_batch** out) {
+  return commit_impl(ctx, values, values_on_host, true, n_log, P, rate_bits, cap_height, salt, salt_on_host, out, 0, ~(u64)0,
+                     coeffs_host_out);
 }
 extern "C" int p2b_commit_from_coeffs(p2b_ctx* ctx, const uint64_t* coeffs, int coeffs_on_host, uint32_t n_log,
                                       uint64_t P, uint32_t rate_bits, uint32_t cap_height, const uint64_t* salt,

@@ -173,3 +173,24 @@ def test_commit_linearity_property(ctx):
     assert np.array_equal(((ra.astype(object) + rb.astype(object)) % P).astype(np.uint64), rs)
     for x in (ba, bb, bs):
         x.close()
+
+
+def test_commit_host_pipeline_with_coefficient_copy_back(ctx):
+    """p2b_commit_from_values_ex: grouped H2D overlapped with the inverse NTT, coefficients copied back to pinned host
+    memory while the tree is built (the data movement of fri/oracle.rs:352-362, 403-407)."""
+    rng = np.random.default_rng(23)
+    for n_log, Pn in [(11, 37), (8, 16), (13, 135)]:
+        n = 1 << n_log
+        values = rand_field(rng, (Pn, n))
+        pinned_in, pinned_out = p2b.PinnedBuffer(Pn * n), p2b.PinnedBuffer(Pn * n)
+        pinned_in.array[:] = values.reshape(-1)
+        hv, hc = pinned_in.array.reshape(Pn, n), pinned_out.array.reshape(Pn, n)
+        b = p2b.PolynomialBatch.from_values(ctx, hv, 3, 4, coeffs_out=hc)
+        e = oracle.batch_from_values(values, 3, 4)
+        assert np.array_equal(b.cap(), e.cap)           # synchronises the stream, which also covers the copy
+        assert np.array_equal(hc, e.coeffs)
+        assert np.array_equal(b.polynomials(), e.coeffs)
+        assert np.array_equal(b.digests(), e.digests)
+        b.close()
+        pinned_in.free()
+        pinned_out.free()
