@@ -59,6 +59,19 @@ __global__ void __launch_bounds__(256) k(u64* out, u32 a0, u32 b0, long long* cy
         float f = __uint_as_float(r[i]);
         asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(__uint_as_float(a)), "f"(__uint_as_float(b)));
         r[i] = __float_as_uint(f);
+      } else if (KIND == 14) { // IMAD.WIDE.U32 without addend (pure 32x32->64)
+        asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo,hi}, %0; mul.wide.u32 %0, lo, %1; }" : "+l"(acc[i]) : "r"(b));
+      } else if (KIND == 15) { // pure mul.wide + 1 IADD3
+        asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo,hi}, %0; mul.wide.u32 %0, lo, %1; }" : "+l"(acc[i]) : "r"(b));
+        asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(r[i]) : "r"(r[(i + 1) % NACC]), "r"(r[(i + 3) % NACC]));
+      } else if (KIND == 16) { // IMAD.WIDE with addend from a different register pair (acc[i] = lo(acc[i]) * b + acc[(i+1)%N])
+        asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo,hi}, %0; mad.wide.u32 %0, lo, %1, %2; }" : "+l"(acc[i]) : "r"(b), "l"(acc[(i + 1) % NACC]));
+      } else if (KIND == 17) { // pure mul.wide + 2 ALU
+        asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo,hi}, %0; mul.wide.u32 %0, lo, %1; }" : "+l"(acc[i]) : "r"(b));
+        asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(r[i]) : "r"(r[(i + 1) % NACC]), "r"(r[(i + 3) % NACC]));
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[i]) : "r"(r[(i + 1) % NACC]), "r"(r[(i + 5) % NACC]));
+      } else if (KIND == 18) { // IMAD.WIDE multiplying by an immediate with a 64-bit accumulate from another pair
+        asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo,hi}, %1; mad.wide.u32 %0, lo, 41, %0; }" : "+l"(acc[i]) : "l"(acc[(i + 1) % NACC]));
       } else if (KIND == 13) { // mix: 1 IMAD.WIDE + 3 ALU
         asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo,hi}, %0; mad.wide.u32 %0, lo, %1, %0; }" : "+l"(acc[i]) : "r"(b));
         asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(r[i]) : "r"(r[(i + 1) % NACC]), "r"(r[(i + 3) % NACC]));
@@ -117,7 +130,7 @@ void run(const char* name, int instr_per_slot, int blocks_per_sm) {
 }
 
 int main() {
-  for (int bps = 4; bps <= 8; bps *= 2) {
+  for (int bps = 8; bps <= 8; bps *= 2) {
     run<0>("IMAD.WIDE.U32", 1, bps);
     run<9>("IMAD.WIDE.U32 imm", 1, bps);
     run<1>("IMAD (lo)", 1, bps);
@@ -132,6 +145,11 @@ int main() {
     run<13>("1 IMAD.WIDE + 3 ALU", 4, bps);
     run<8>("1 IMAD lo + 1 LOP3", 2, bps);
     run<11>("1 IMAD.WIDE + 1 IMAD lo", 2, bps);
+    run<14>("mul.wide (no addend)", 1, bps);
+    run<16>("IMAD.WIDE addend other pair", 1, bps);
+    run<18>("IMAD.WIDE imm, addend other pair", 1, bps);
+    run<15>("1 mul.wide + 1 IADD3", 2, bps);
+    run<17>("1 mul.wide + 2 ALU", 3, bps);
     printf("\n");
   }
   return 0;
