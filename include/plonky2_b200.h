@@ -66,6 +66,9 @@ uint64_t p2b_ctx_launch_count(const p2b_ctx* ctx);
 /* Live timing of the dominant kernel (leaf hashing) with CUDA events on the stream it is launched on: enable, run
  * commits, then read the summed duration and the number of launches timed (bench.py's roofline figure). */
 int p2b_ctx_time_leaf_hash(p2b_ctx* ctx, int enable);
+/* Test hook: the NTT kernels use an optimistic field reduction and redo a tile exactly when it reports its rare case
+ * (probability ~2^-32 per butterfly); enabling this makes every tile take that redo path. */
+int p2b_ctx_debug_force_exact_redo(p2b_ctx* ctx, int enable);
 int p2b_ctx_leaf_hash_time(p2b_ctx* ctx, double* total_ms, uint64_t* launches);
 
 /* ---------------------------------------------------------------------------------------------------

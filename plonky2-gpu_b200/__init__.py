@@ -116,6 +116,7 @@ def lib():
         "p2b_ctx_synchronize": (i, [vp]),
         "p2b_ctx_launch_count": (u64, [vp]),
         "p2b_ctx_time_leaf_hash": (i, [vp, i]),
+        "p2b_ctx_debug_force_exact_redo": (i, [vp, i]),
         "p2b_ctx_leaf_hash_time": (i, [vp, C.POINTER(C.c_double), C.POINTER(u64)]),
         "p2b_commit_from_values": (i, [vp, vp, i, u32, u64, u32, u32, vp, i, C.POINTER(vp)]),
         "p2b_commit_from_coeffs": (i, [vp, vp, i, u32, u64, u32, u32, vp, i, C.POINTER(vp)]),
@@ -254,6 +255,9 @@ class Context:
     @property
     def launch_count(self):
         return int(lib().p2b_ctx_launch_count(self.handle))
+
+    def debug_force_exact_redo(self, enable=True):
+        _check(lib().p2b_ctx_debug_force_exact_redo(self.handle, 1 if enable else 0))
 
     def time_leaf_hash(self, enable=True):
         _check(lib().p2b_ctx_time_leaf_hash(self.handle, 1 if enable else 0))

@@ -62,8 +62,10 @@ __device__ __forceinline__ void load_hash(const u64* src, u64 h[4]) {
   h[0] = a.x; h[1] = a.y; h[2] = b.x; h[3] = b.y;
 }
 
-// hash_or_noop of one leaf whose element j is at base[j * col_stride].  Result canonical.
-__device__ __forceinline__ void hash_leaf(const u64* __restrict__ base, u64 col_stride, u32 leaf_len, u64 out[4]) {
+// hash_or_noop of one leaf whose element j is at base[j * col_stride].  Result canonical.  M selects the exact or the
+// optimistic field reduction (gl64.cuh); with the optimistic one the caller must check m.rare and redo exactly.
+template <class M>
+__device__ __forceinline__ void hash_leaf(const u64* __restrict__ base, u64 col_stride, u32 leaf_len, u64 out[4], M& m) {
   if (leaf_len <= 4) {  // plonk/config.rs:57-63: copy canonical values, zero pad
 #pragma unroll
     for (u32 i = 0; i < 4; i++) out[i] = i < leaf_len ? gl::canon(__ldg(base + i * col_stride)) : 0;
@@ -81,7 +83,7 @@ __device__ __forceinline__ void hash_leaf(const u64* __restrict__ base, u64 col_
     for (int i = 0; i < 8; i++)
       if ((u32)i < left) s[i] = __ldg(p + i * col_stride);
     p += 8 * col_stride;
-    poseidon::permute(s);
+    poseidon::permute(s, m);
   }
 #pragma unroll
   for (int i = 0; i < 4; i++) out[i] = gl::canon(s[i]);
@@ -93,7 +95,10 @@ __device__ __forceinline__ void hash_leaf(const u64* __restrict__ base, u64 col_
 #ifndef P2B_HASH_BLOCK
 #define P2B_HASH_BLOCK 128
 #endif
-__global__ void __launch_bounds__(P2B_HASH_BLOCK)
+#ifndef P2B_HASH_MIN_BLOCKS
+#define P2B_HASH_MIN_BLOCKS 7
+#endif
+__global__ void __launch_bounds__(P2B_HASH_BLOCK, P2B_HASH_MIN_BLOCKS)
 hash_leaves_kernel(const u64* __restrict__ leaves, u64 row_stride, u64 col_stride, u32 leaf_len, u64 count,
                    u64 leaf_index0, TreeShape shape, u64* __restrict__ digests, u64* __restrict__ cap) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -101,12 +106,20 @@ hash_leaves_kernel(const u64* __restrict__ leaves, u64 row_stride, u64 col_strid
   const bool live = i < count;
   if (!live) i = count - 1;
   u64 h[4];
-  hash_leaf(leaves + i * row_stride, col_stride, leaf_len, h);
+#ifndef P2B_EXACT_ONLY
+  gl::Optimistic fast;
+  hash_leaf(leaves + i * row_stride, col_stride, leaf_len, h, fast);
+  if (fast.rare)  // ~2^-32 per multiplication on random data: redo this leaf with fully repaid reductions
+#endif
+  {
+    gl::Exact exact;
+    hash_leaf(leaves + i * row_stride, col_stride, leaf_len, h, exact);
+  }
   if (live) store_hash(node_slot(shape, digests, cap, 0, leaf_index0 + i), h);
 }
 
 // One thread per node of layer `l` (l >= 1): parent of nodes 2Q, 2Q+1 of layer l-1.
-__global__ void __launch_bounds__(P2B_HASH_BLOCK)
+__global__ void __launch_bounds__(P2B_HASH_BLOCK, P2B_HASH_MIN_BLOCKS)
 merkle_layer_kernel(TreeShape shape, u32 l, u64 node0, u64 count, u64* __restrict__ digests, u64* __restrict__ cap) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < count;
@@ -116,19 +129,37 @@ merkle_layer_kernel(TreeShape shape, u32 l, u64 node0, u64 count, u64* __restric
   u64 a[4], b[4], h[4];
   load_hash(left, a);
   load_hash(left + 4, b);
-  poseidon::two_to_one(a, b, h);
+#ifndef P2B_EXACT_ONLY
+  gl::Optimistic fast;
+  poseidon::two_to_one(a, b, h, fast);
+  if (fast.rare)
+#endif
+  {
+    gl::Exact exact;
+    poseidon::two_to_one(a, b, h, exact);
+  }
   if (live) store_hash(node_slot(shape, digests, cap, l, Q), h);
 }
 
 // Batched permutation (test / micro-benchmark entry): states[i][12] -> permuted, canonical.
-__global__ void __launch_bounds__(P2B_HASH_BLOCK) permute_kernel(u64* __restrict__ states, u64 count, int reps) {
+__global__ void __launch_bounds__(P2B_HASH_BLOCK, P2B_HASH_MIN_BLOCKS) permute_kernel(u64* __restrict__ states, u64 count, int reps) {
   u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < count;
   if (!live) i = count - 1;
   u64 s[12];
+#ifndef P2B_EXACT_ONLY
+  gl::Optimistic fast;
 #pragma unroll
   for (int k = 0; k < 12; k++) s[k] = states[i * 12 + k];
-  for (int r = 0; r < reps; r++) poseidon::permute(s);
+  for (int r = 0; r < reps; r++) poseidon::permute(s, fast);
+  if (fast.rare)
+#endif
+  {
+    gl::Exact exact;
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = states[i * 12 + k];
+    for (int r = 0; r < reps; r++) poseidon::permute(s, exact);
+  }
 #pragma unroll
   for (int k = 0; k < 12; k++)
     if (live) states[i * 12 + k] = gl::canon(s[k]);

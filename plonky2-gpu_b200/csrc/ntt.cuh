@@ -43,9 +43,12 @@ struct LevelScale {
   u64 sigma[MAX_LEVELS];  // sigma[s] multiplies U at level s of the sub-problem (all ones for a plain NTT)
 };
 
-// (u, v) <- (u + z v, u - z v)
-__device__ __forceinline__ void butterfly(u64& u, u64& v, u64 z) {
-  u64 t = gl::mul(z, v);
+// (u, v) <- (u + z v, u - z v).  M: exact or optimistic reduction (gl64.cuh); a kernel that runs the optimistic form
+// checks the CTA-wide OR of m.rare before storing and, if set (~2^-32 per butterfly), reloads its tile and redoes it
+// with the exact form, so results are bit-exact for every input.
+template <class M>
+__device__ __forceinline__ void butterfly(u64& u, u64& v, u64 z, M& m) {
+  u64 t = gl::mul(z, v, m);
   u64 a = gl::add(u, t);
   v = gl::sub(u, t);
   u = a;
@@ -65,9 +68,9 @@ __global__ void build_twiddles_kernel(u64* __restrict__ U, u64 count, const u64*
 // ---- in-shared-memory levels --------------------------------------------------------------------------
 // x: [2^L][TP] (t fastest, TP >= T), W: twiddles of the tile, W[(1 << a) - 1 + lb] for local level a, local
 // block lb.  Runs local levels [a, a + R) with R in {1,2,3} in registers.  All threads must call.
-template <int R>
+template <int R, class M>
 __device__ __forceinline__ void radix_group(u64* __restrict__ x, const u64* __restrict__ W, int L, int a, int T,
-                                            int TP, int tid, int nthreads) {
+                                            int TP, int tid, int nthreads, M& mode) {
   const int ll_bits = L - a - R;
   const int items = (1 << (L - R)) * T;
   for (int it = tid; it < items; it += nthreads) {
@@ -86,7 +89,7 @@ __device__ __forceinline__ void radix_group(u64* __restrict__ x, const u64* __re
       for (int m = 0; m < (1 << R); m++) {
         if (m & half) continue;
         u64 z = W[(1 << (a + u)) - 1 + (lh << u) + (m >> (R - u))];
-        butterfly(v[m], v[m + half], z);
+        butterfly(v[m], v[m + half], z, mode);
       }
     }
 #pragma unroll
@@ -95,18 +98,19 @@ __device__ __forceinline__ void radix_group(u64* __restrict__ x, const u64* __re
 }
 
 // all L levels of the tile; ends with a __syncthreads
-__device__ __forceinline__ void run_levels(u64* x, const u64* W, int L, int T, int TP, int tid, int nthreads) {
+template <class M>
+__device__ __forceinline__ void run_levels(u64* x, const u64* W, int L, int T, int TP, int tid, int nthreads, M& m) {
   int a = 0;
   while (a < L) {
     int rem = L - a;
     if (rem >= 3 && rem != 4) {
-      radix_group<3>(x, W, L, a, T, TP, tid, nthreads);
+      radix_group<3>(x, W, L, a, T, TP, tid, nthreads, m);
       a += 3;
     } else if (rem >= 2) {
-      radix_group<2>(x, W, L, a, T, TP, tid, nthreads);
+      radix_group<2>(x, W, L, a, T, TP, tid, nthreads, m);
       a += 2;
     } else {
-      radix_group<1>(x, W, L, a, T, TP, tid, nthreads);
+      radix_group<1>(x, W, L, a, T, TP, tid, nthreads, m);
       a += 1;
     }
     __syncthreads();
@@ -135,6 +139,7 @@ struct PassArgs {
   const u64* U;
   u32 scaled;       // use sc.sigma
   u32 ncols;
+  u32 force_redo;   // test hook: take the exact-redo path as if an optimistic reduction had reported a rare case
 };
 
 // ---- K1: strided pass (s0 + L < k).  grid.x = 2^s0 * (stride / T) tiles, grid.y = columns -------------
@@ -161,7 +166,17 @@ __global__ void __launch_bounds__(512) ntt_strided_pass_kernel(PassArgs p, Level
     x[i] = src[(u64)l * stride + t];
   }
   __syncthreads();
-  run_levels(x, W, L, T, T, tid, nt);
+  gl::Optimistic fast;
+  run_levels(x, W, L, T, T, tid, nt, fast);
+  if (__syncthreads_or(fast.rare | (p.force_redo != 0))) {  // the source tile is still intact (nothing stored yet): redo it exactly
+    for (int i = tid; i < (T << L); i += nt) {
+      int t = i % T, l = i / T;
+      x[i] = src[(u64)l * stride + t];
+    }
+    __syncthreads();
+    gl::Exact exact;
+    run_levels(x, W, L, T, T, tid, nt, exact);
+  }
   for (int i = tid; i < (T << L); i += nt) {
     int t = i % T, l = i / T;
     dst[(u64)l * stride + t] = x[i];
@@ -193,7 +208,17 @@ __global__ void __launch_bounds__(512) ntt_final_pass_kernel(PassArgs p, LevelSc
     x[l * TP + c] = c < nc ? p.src[(u64)(c0 + c) * p.src_cs + base + l] : 0;
   }
   __syncthreads();
-  run_levels(x, W, L, C, TP, tid, nt);
+  gl::Optimistic fast;
+  run_levels(x, W, L, C, TP, tid, nt, fast);
+  if (__syncthreads_or(fast.rare | (p.force_redo != 0))) {
+    for (int i = tid; i < (C << L); i += nt) {
+      int l = i & ((1 << L) - 1), c = i >> L;
+      x[l * TP + c] = c < nc ? p.src[(u64)(c0 + c) * p.src_cs + base + l] : 0;
+    }
+    __syncthreads();
+    gl::Exact exact;
+    run_levels(x, W, L, C, TP, tid, nt, exact);
+  }
   if (MODE == MODE_COLMAJOR) {
     for (int i = tid; i < (C << L); i += nt) {
       int l = i & ((1 << L) - 1), c = i >> L;
@@ -245,7 +270,8 @@ __global__ void __launch_bounds__(512) intt_final_pass_kernel(PassArgs p, u64 n_
       u64 q = s0 ? (__brevll(qp0 + j) >> (64 - s0)) : 0;
       u64 z = __ldg(p.U + ((q << a) + lh));
       u64 u = x[l0 * J + j], v = x[l1 * J + j];
-      butterfly(u, v, z);
+      gl::Exact exact;
+      butterfly(u, v, z, exact);
       x[l0 * J + j] = u;
       x[l1 * J + j] = v;
     }

@@ -109,6 +109,7 @@ struct p2b_ctx {
   u64* scratch = nullptr;
   u64 scratch_elems = 0;
   u64 launches = 0;
+  bool debug_force_redo = false;  // test hook (p2b_ctx_debug_force_exact_redo)
   // optional per-kernel timing of the dominant kernel (leaf hashing): event pairs on the launching stream
   bool time_hash = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> hash_events;
@@ -256,6 +257,11 @@ extern "C" int p2b_ctx_synchronize(p2b_ctx* c) {
   return P2B_OK;
 }
 extern "C" uint64_t p2b_ctx_launch_count(const p2b_ctx* c) { return c ? c->launches : 0; }
+extern "C" int p2b_ctx_debug_force_exact_redo(p2b_ctx* c, int enable) {
+  if (!c) return fail(P2B_ERR_INVALID, "ctx is NULL");
+  c->debug_force_redo = enable != 0;
+  return P2B_OK;
+}
 extern "C" int p2b_ctx_time_leaf_hash(p2b_ctx* c, int enable) {
   if (!c) return fail(P2B_ERR_INVALID, "ctx is NULL");
   c->time_hash = enable != 0;
@@ -350,6 +356,7 @@ static int run_ifft(p2b_ctx* c, const u64* src, u64* dst, u64* tmp, u32 k, u64 P
   a.U = c->U_inv;
   a.scaled = 0;
   a.ncols = (u32)P;
+  a.force_redo = c->debug_force_redo;
   const u64* cur = src;
   for (u32 i = 0; i < pl.n_strided; i++) {
     a.src = cur;
@@ -394,6 +401,7 @@ static int run_lde_block(p2b_ctx* c, cudaStream_t st, const u64* coeffs, u64 coe
   a.U = c->U_fwd;
   a.scaled = 1;
   a.ncols = (u32)P;
+  a.force_redo = c->debug_force_redo;
   const u64* cur = coeffs;
   u64 cur_cs = coeffs_cs;
   for (u32 i = 0; i < pl.n_strided; i++) {

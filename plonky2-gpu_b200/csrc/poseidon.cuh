@@ -46,11 +46,16 @@ __device__ __forceinline__ constexpr u32 mds_circ(int i) {
 static constexpr u32 MDS_DIAG0 = 8;
 
 // x^7 (sbox_monomial, poseidon.rs:525-532)
+template <class M>
+__device__ __forceinline__ u64 sbox(u64 x, M& m) {
+  u64 x2 = gl::sqr(x, m);
+  u64 x4 = gl::sqr(x2, m);
+  u64 x3 = gl::mul(x, x2, m);
+  return gl::mul(x3, x4, m);
+}
 __device__ __forceinline__ u64 sbox(u64 x) {
-  u64 x2 = gl::sqr(x);
-  u64 x4 = gl::sqr(x2);
-  u64 x3 = gl::mul(x, x2);
-  return gl::mul(x3, x4);
+  gl::Exact m;
+  return sbox(x, m);
 }
 
 // out[r] = sum_i circ[i] * s[(i+r)%12] + diag[r]*s[r] + addc[r]   (mds_row_shf + mds_layer, then the next
@@ -141,14 +146,15 @@ __device__ __forceinline__ void mds_layer(u64 (&s)[12], const u64* __restrict__ 
 // streaming through the permutation, instruction fetch stalls ("no_instruction" in ncu) dominate as soon as the
 // hot code exceeds the ~32 KB instruction cache, so the 12 S-boxes are a rolled loop of 3 x 4 with a register
 // rotation (24 moves per iteration) instead of 12 inlined copies (13 KB of SASS).
-__device__ __forceinline__ void sbox_layer(u64 (&s)[12]) {
+template <class M>
+__device__ __forceinline__ void sbox_layer(u64 (&s)[12], M& m) {
 #ifdef P2B_SBOX_UNROLLED
 #pragma unroll
-  for (int i = 0; i < 12; i++) s[i] = sbox(s[i]);
+  for (int i = 0; i < 12; i++) s[i] = sbox(s[i], m);
 #else
 #pragma unroll 1
   for (int g = 0; g < 3; g++) {
-    u64 t0 = sbox(s[0]), t1 = sbox(s[1]), t2 = sbox(s[2]), t3 = sbox(s[3]);
+    u64 t0 = sbox(s[0], m), t1 = sbox(s[1], m), t2 = sbox(s[2], m), t3 = sbox(s[3], m);
 #pragma unroll
     for (int i = 0; i < 8; i++) s[i] = s[i + 4];
     s[8] = t0;
@@ -159,6 +165,11 @@ __device__ __forceinline__ void sbox_layer(u64 (&s)[12]) {
 #endif
 }
 
+__device__ __forceinline__ void sbox_layer(u64 (&s)[12]) {
+  gl::Exact m;
+  sbox_layer(s, m);
+}
+
 // 128-bit accumulate helper for the partial-round dot products: (acc_lo, acc_hi, acc_top) += a*b
 __device__ __forceinline__ void mac160(u64& lo, u64& hi, u32& top, u64 a, u64 b) {
   u64 pl, ph;
@@ -166,9 +177,14 @@ __device__ __forceinline__ void mac160(u64& lo, u64& hi, u32& top, u64 a, u64 b)
   asm("{ add.cc.u64 %0, %0, %3; addc.cc.u64 %1, %1, %4; addc.u32 %2, %2, 0; }" : "+l"(lo), "+l"(hi), "+r"(top) : "l"(pl), "l"(ph));
 }
 // reduce_u160 (poseidon.rs:40-47)
-__device__ __forceinline__ u64 reduce160(u64 lo, u64 hi, u32 top) {
+template <class M>
+__device__ __forceinline__ u64 reduce160(u64 lo, u64 hi, u32 top, M& m) {
   u64 reduced_hi = gl::reduce96(hi, top);
-  return gl::reduce128(lo, reduced_hi);
+  return gl::reduce128(lo, reduced_hi, m);
+}
+__device__ __forceinline__ u64 reduce160(u64 lo, u64 hi, u32 top) {
+  gl::Exact m;
+  return reduce160(lo, hi, top, m);
 }
 
 // Optional block-wide barrier at every round boundary (P2B_SYNC_ROUNDS): keeps all warps of a CTA inside the same
@@ -184,7 +200,8 @@ __device__ __forceinline__ void round_sync() {
 // mds_partial_layer_init (poseidon.rs:310-337): s[0] unchanged; s[c] = sum_r s[r] * init[r-1][c-1].
 // Rolled over the output column c (keeps ~24 KB of straight-line code out of the instruction cache); the results
 // are pushed through a shift register so no register array is indexed dynamically.
-__device__ __forceinline__ void partial_layer_init(u64 (&s)[12]) {
+template <class M>
+__device__ __forceinline__ void partial_layer_init(u64 (&s)[12], M& m) {
 #ifdef P2B_INIT_UNROLLED
   u64 t[12];
   t[0] = s[0];
@@ -194,7 +211,7 @@ __device__ __forceinline__ void partial_layer_init(u64 (&s)[12]) {
     u32 top = 0;
 #pragma unroll
     for (int r = 1; r < 12; r++) mac160(lo, hi, top, s[r], C.init[(r - 1) * 11 + (c - 1)]);
-    t[c] = reduce160(lo, hi, top);
+    t[c] = reduce160(lo, hi, top, m);
   }
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = t[i];
@@ -208,7 +225,7 @@ __device__ __forceinline__ void partial_layer_init(u64 (&s)[12]) {
     u32 top = 0;
 #pragma unroll
     for (int r = 1; r < 12; r++) mac160(lo, hi, top, s[r], C.init[(r - 1) * 11 + c]);
-    u64 v = reduce160(lo, hi, top);
+    u64 v = reduce160(lo, hi, top, m);
 #pragma unroll
     for (int i = 1; i < 11; i++) t[i] = t[i + 1];
     t[11] = v;
@@ -220,7 +237,8 @@ __device__ __forceinline__ void partial_layer_init(u64 (&s)[12]) {
 
 // mds_partial_layer_fast (poseidon.rs:398-427) for partial round r; s0 = the S-boxed (and constant-added) lane 0:
 //   s[0] <- 25*s0 + sum_i w_hat[r][i-1] * s[i]   (u160 accumulator),   s[i] <- s[i] + s0 * vs[r][i-1]
-__device__ __forceinline__ void partial_layer_fast(u64 (&s)[12], u64 s0, int r) {
+template <class M>
+__device__ __forceinline__ void partial_layer_fast(u64 (&s)[12], u64 s0, int r, M& m) {
   u64 lo, hi;
   u32 top = 0;
   {
@@ -236,15 +254,24 @@ __device__ __forceinline__ void partial_layer_fast(u64 (&s)[12], u64 s0, int r) 
   }
 #pragma unroll
   for (int i = 1; i < 12; i++) mac160(lo, hi, top, s[i], C.w_hats[r * 11 + i - 1]);
-  u64 d = reduce160(lo, hi, top);
+  u64 d = reduce160(lo, hi, top, m);
 #pragma unroll
-  for (int i = 1; i < 12; i++) s[i] = gl::mul_add(s0, C.vs[r * 11 + i - 1], s[i]);
+  for (int i = 1; i < 12; i++) s[i] = gl::mul_add(s0, C.vs[r * 11 + i - 1], s[i], m);
   s[0] = d;
+}
+__device__ __forceinline__ void partial_layer_init(u64 (&s)[12]) {
+  gl::Exact m;
+  partial_layer_init(s, m);
+}
+__device__ __forceinline__ void partial_layer_fast(u64 (&s)[12], u64 s0, int r) {
+  gl::Exact m;
+  partial_layer_fast(s, s0, r, m);
 }
 
 // The permutation.  Input: any u64 representatives; output: u64 representatives (NOT canonicalised --
 // callers canonicalise what they store).
-__device__ __forceinline__ void permute(u64 (&s)[12]) {
+template <class M>
+__device__ __forceinline__ void permute(u64 (&s)[12], M& m) {
   // constant layer of round 0 up front; every later constant layer is folded into the preceding MDS.
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl::add_canonical(s[i], C.rc[i]);
@@ -254,17 +281,17 @@ __device__ __forceinline__ void permute(u64 (&s)[12]) {
 #pragma unroll 1
     for (int r = 0; r < 4; r++) {
       round_sync();
-      sbox_layer(s);
+      sbox_layer(s, m);
       mds_layer(s, &C.post[12 * (half * 4 + r)]);
     }
     if (half == 0) {
       // ---- partial rounds (poseidon.rs:574-588); first-round constants were folded into post[3] ----
-      partial_layer_init(s);
+      partial_layer_init(s, m);
 #pragma unroll 1
       for (int r = 0; r < 22; r++) {
         round_sync();
-        u64 s0 = gl::add_canonical(sbox(s[0]), C.partial_rc[r]);
-        partial_layer_fast(s, s0, r);
+        u64 s0 = gl::add_canonical(sbox(s[0], m), C.partial_rc[r]);
+        partial_layer_fast(s, s0, r, m);
       }
       // constant layer of round 26 (first of the closing full rounds)
 #pragma unroll
@@ -273,8 +300,15 @@ __device__ __forceinline__ void permute(u64 (&s)[12]) {
   }
 }
 
+// exact permutation (every reduction fully repaid)
+__device__ __forceinline__ void permute(u64 (&s)[12]) {
+  gl::Exact m;
+  permute(s, m);
+}
+
 // compress / two_to_one (hashing.rs:65-72): perm([l, r, 0,0,0,0])[0..4]; output canonical.
-__device__ __forceinline__ void two_to_one(const u64 l[4], const u64 r[4], u64 out[4]) {
+template <class M>
+__device__ __forceinline__ void two_to_one(const u64 l[4], const u64 r[4], u64 out[4], M& m) {
   u64 s[12];
 #pragma unroll
   for (int i = 0; i < 4; i++) {
@@ -282,7 +316,7 @@ __device__ __forceinline__ void two_to_one(const u64 l[4], const u64 r[4], u64 o
     s[4 + i] = r[i];
     s[8 + i] = 0;
   }
-  permute(s);
+  permute(s, m);
 #pragma unroll
   for (int i = 0; i < 4; i++) out[i] = gl::canon(s[i]);
 }

@@ -24,7 +24,9 @@ def rand_field(rng, shape):
 
 
 EDGE = np.array([0, 1, 2, P - 1, P - 2, P, P + 1, 2**64 - 1, 2**32 - 1, 2**32, 2**32 + 1, 2**63,
-                 0xFFFFFFFF00000000, 0xFFFFFFFE00000001, 0x00000000FFFFFFFF, 0xFFFFFFFFFFFFFFFE], dtype=np.uint64)
+                 0xFFFFFFFF00000000, 0xFFFFFFFE00000001, 0x00000000FFFFFFFF, 0xFFFFFFFFFFFFFFFE,
+                 # products of these hit the rarely-taken repayment of reduce128 (lo + hi_lo*eps < hi_hi): 2^48 * 2^48 = 2^96
+                 2**48, 3 * 2**48, 2**49 + 2**48, 0xFFFF * 2**48], dtype=np.uint64)
 
 
 @pytest.mark.parametrize("op", ["add", "sub", "mul", "mul_add", "add_canonical", "sub_canonical"])
@@ -56,7 +58,7 @@ def test_poseidon_reference_known_answers(ctx):
 def test_poseidon_random_and_noncanonical(ctx):
     rng = np.random.default_rng(12)
     s = rng.integers(0, 2**64, size=(2000, 12), dtype=np.uint64)  # includes non-canonical representatives
-    s[:16] = EDGE[:, None]
+    s[:EDGE.size] = EDGE[:, None]
     got = ctx.poseidon(s)
     for i in range(0, 2000, 7):
         assert np.array_equal(got[i], oracle.poseidon(s[i])), i
@@ -194,3 +196,51 @@ def test_commit_host_pipeline_with_coefficient_copy_back(ctx):
         b.close()
         pinned_in.free()
         pinned_out.free()
+
+
+def test_poseidon_optimistic_reduction_falls_back_exactly(ctx):
+    """The hash kernels run an optimistic reduce128 (gl64.cuh) and redo a leaf / node / state exactly when the rare
+    borrow case fires.  Force it: a state lane equal to 2^48 - RC[0][lane] makes the first S-box square 2^48 (x*x = 2^96:
+    lo = 0, hi = 2^32), for the permutation entry, a leaf hash and a 2-to-1 compression."""
+    from oracle import poseidon_params as PP
+    rng = np.random.default_rng(29)
+    states = rng.integers(0, P, size=(64, 12), dtype=np.uint64)
+    for k in range(64):
+        lane = k % 12
+        states[k, lane] = (2**48 * (1 + k // 12) - PP.ROUND_CONSTANTS[lane]) % P
+    got = ctx.poseidon(states)
+    for k in range(64):
+        assert np.array_equal(got[k], oracle.poseidon(states[k])), k
+    # leaves whose first absorbed chunk (lanes 0..7) triggers the case, in every 3rd leaf; capacity lanes start at 0,
+    # so lanes 8..11 would need RC = 2^48 and are left alone
+    leaves = rng.integers(0, P, size=(128, 20), dtype=np.uint64)
+    for r in range(0, 128, 3):
+        lane = r % 8
+        leaves[r, lane] = (2**48 - PP.ROUND_CONSTANTS[lane]) % P
+    d, cap = ctx.merkle_tree(leaves, 2)
+    ed, ecap = oracle.merkle_tree(leaves, 2)
+    assert np.array_equal(d, ed) and np.array_equal(cap, ecap)
+    # 4-element leaves are copied verbatim (hash_or_noop), so layer 1 compresses exactly these crafted values
+    small = rng.integers(0, P, size=(64, 4), dtype=np.uint64)
+    for r in range(0, 64, 2):
+        small[r, r % 4] = (2**48 - PP.ROUND_CONSTANTS[r % 4]) % P
+    d, cap = ctx.merkle_tree(small, 0)
+    ed, ecap = oracle.merkle_tree(small, 0)
+    assert np.array_equal(d, ed) and np.array_equal(cap, ecap)
+
+
+def test_ntt_exact_redo_path(ctx):
+    """NTT tiles run optimistic butterflies and are redone exactly when a reduction reports its rare case; the test hook
+    forces that path for every tile (strided, final-rows) and the results must not change."""
+    rng = np.random.default_rng(31)
+    values = rand_field(rng, (9, 1 << 12))
+    ctx.debug_force_exact_redo(True)
+    try:
+        b = p2b.PolynomialBatch.from_values(ctx, values, 3, 4)
+        e = oracle.batch_from_values(values, 3, 4)
+        assert np.array_equal(b.polynomials(), e.coeffs)
+        assert np.array_equal(b.leaves(), e.leaves)
+        assert np.array_equal(b.cap(), e.cap)
+        b.close()
+    finally:
+        ctx.debug_force_exact_redo(False)
