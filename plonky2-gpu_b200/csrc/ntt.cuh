@@ -54,6 +54,14 @@ __device__ __forceinline__ void butterfly(u64& u, u64& v, u64 z, M& m) {
   u = a;
 }
 
+// to_canonical_u64 on the carry chain: x >= p  <=>  x + eps wraps, and then x - p == x + eps (mod 2^64)
+__device__ __forceinline__ u64 canon_fast(u64 x) {
+  u64 t;
+  u32 c;
+  asm("{ add.cc.u64 %0, %2, 0xffffffff; addc.u32 %1, 0, 0; }" : "=l"(t), "=r"(c) : "l"(x));
+  return c ? t : x;
+}
+
 // U[b] = prod_{m in bits(b)} root(m + 2);  roots[j] = primitive_root_of_unity(j) (or its inverse).
 __global__ void build_twiddles_kernel(u64* __restrict__ U, u64 count, const u64* __restrict__ roots) {
   u64 b = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -68,8 +76,19 @@ __global__ void build_twiddles_kernel(u64* __restrict__ U, u64 count, const u64*
 // ---- in-shared-memory levels --------------------------------------------------------------------------
 // x: [2^L][TP] (t fastest, TP >= T), W: twiddles of the tile, W[(1 << a) - 1 + lb] for local level a, local
 // block lb.  Runs local levels [a, a + R) with R in {1,2,3} in registers.  All threads must call.
-template <int R, class M>
-__device__ __forceinline__ void radix_group(u64* __restrict__ x, const u64* __restrict__ W, int L, int a, int T,
+// twiddle accessors: tw(level, block) for local level / local block of the tile
+struct StagedTwiddles {  // W[(1 << level) - 1 + block] in shared memory (one evaluation-tree node per CTA)
+  const u64* W;
+  __device__ __forceinline__ u64 operator()(int level, int block) const { return W[(1 << level) - 1 + block]; }
+};
+struct GlobalTwiddles {  // U[(q << level) + block] through L1: every lane of the tile is a different tree node q
+  const u64* U;
+  u64 q;
+  __device__ __forceinline__ u64 operator()(int level, int block) const { return __ldg(U + ((q << level) + block)); }
+};
+
+template <int R, class M, class TW>
+__device__ __forceinline__ void radix_group(u64* __restrict__ x, const TW& tw, int L, int a, int T,
                                             int TP, int tid, int nthreads, M& mode) {
   const int ll_bits = L - a - R;
   const int items = (1 << (L - R)) * T;
@@ -88,7 +107,7 @@ __device__ __forceinline__ void radix_group(u64* __restrict__ x, const u64* __re
 #pragma unroll
       for (int m = 0; m < (1 << R); m++) {
         if (m & half) continue;
-        u64 z = W[(1 << (a + u)) - 1 + (lh << u) + (m >> (R - u))];
+        u64 z = tw(a + u, (lh << u) + (m >> (R - u)));
         butterfly(v[m], v[m + half], z, mode);
       }
     }
@@ -98,8 +117,8 @@ __device__ __forceinline__ void radix_group(u64* __restrict__ x, const u64* __re
 }
 
 // all L levels of the tile; ends with a __syncthreads
-template <class M>
-__device__ __forceinline__ void run_levels(u64* x, const u64* W, int L, int T, int TP, int tid, int nthreads, M& m) {
+template <class M, class TW>
+__device__ __forceinline__ void run_levels(u64* x, const TW& W, int L, int T, int TP, int tid, int nthreads, M& m) {
   int a = 0;
   while (a < L) {
     int rem = L - a;
@@ -161,25 +180,27 @@ __global__ void __launch_bounds__(512) ntt_strided_pass_kernel(PassArgs p, Level
   const int tid = threadIdx.x, nt = blockDim.x;
 
   stage_twiddles(W, p.U, sc, p.scaled, p.s0, L, (p.block_base << p.s0) + Bhi, tid, nt);
-  for (int i = tid; i < (T << L); i += nt) {
-    int t = i % T, l = i / T;
-    x[i] = src[(u64)l * stride + t];
+  // thread -> (row l0 + k * rows_per_iter, position t): the pointer advances by a fixed stride per iteration, so the
+  // copy loops are a load/store, a pointer add and a compare per element (nt is a multiple of T)
+  const int t = tid % T, l0 = tid / T, rows_per_iter = nt / T;
+  const u64 step = (u64)rows_per_iter * stride;
+  {
+    const u64* sp = src + (u64)l0 * stride + t;
+    for (int i = tid; i < (T << L); i += nt, sp += step) x[i] = *sp;
   }
   __syncthreads();
   gl::Optimistic fast;
-  run_levels(x, W, L, T, T, tid, nt, fast);
+  run_levels(x, StagedTwiddles{W}, L, T, T, tid, nt, fast);
   if (__syncthreads_or(fast.rare | (p.force_redo != 0))) {  // the source tile is still intact (nothing stored yet): redo it exactly
-    for (int i = tid; i < (T << L); i += nt) {
-      int t = i % T, l = i / T;
-      x[i] = src[(u64)l * stride + t];
-    }
+    const u64* sp = src + (u64)l0 * stride + t;
+    for (int i = tid; i < (T << L); i += nt, sp += step) x[i] = *sp;
     __syncthreads();
     gl::Exact exact;
-    run_levels(x, W, L, T, T, tid, nt, exact);
+    run_levels(x, StagedTwiddles{W}, L, T, T, tid, nt, exact);
   }
-  for (int i = tid; i < (T << L); i += nt) {
-    int t = i % T, l = i / T;
-    dst[(u64)l * stride + t] = x[i];
+  {
+    u64* dp = dst + (u64)l0 * stride + t;
+    for (int i = tid; i < (T << L); i += nt, dp += step) *dp = x[i];
   }
 }
 
@@ -203,31 +224,43 @@ __global__ void __launch_bounds__(512) ntt_final_pass_kernel(PassArgs p, LevelSc
   const u64 base = q << L;
 
   stage_twiddles(W, p.U, sc, p.scaled, p.s0, L, (p.block_base << p.s0) + q, tid, nt);
-  for (int i = tid; i < (C << L); i += nt) {
-    int l = i & ((1 << L) - 1), c = i >> L;
-    x[l * TP + c] = c < nc ? p.src[(u64)(c0 + c) * p.src_cs + base + l] : 0;
-  }
+  auto load_tile = [&]() {
+    // consecutive threads read consecutive positions of a column (coalesced); the C column loads of a position are
+    // issued back to back (predicated, independent) before anything is stored to shared memory
+    const u64* sp = p.src + (u64)c0 * p.src_cs + base;
+    for (int l = tid; l < (1 << L); l += nt) {
+      u64 v[C];
+#pragma unroll
+      for (int c = 0; c < C; c++) v[c] = c < nc ? sp[(u64)c * p.src_cs + l] : 0;
+#pragma unroll
+      for (int c = 0; c < C; c++) x[l * TP + c] = v[c];
+    }
+  };
+  load_tile();
   __syncthreads();
   gl::Optimistic fast;
-  run_levels(x, W, L, C, TP, tid, nt, fast);
+  run_levels(x, StagedTwiddles{W}, L, C, TP, tid, nt, fast);
   if (__syncthreads_or(fast.rare | (p.force_redo != 0))) {
-    for (int i = tid; i < (C << L); i += nt) {
-      int l = i & ((1 << L) - 1), c = i >> L;
-      x[l * TP + c] = c < nc ? p.src[(u64)(c0 + c) * p.src_cs + base + l] : 0;
-    }
+    load_tile();
     __syncthreads();
     gl::Exact exact;
-    run_levels(x, W, L, C, TP, tid, nt, exact);
+    run_levels(x, StagedTwiddles{W}, L, C, TP, tid, nt, exact);
   }
   if (MODE == MODE_COLMAJOR) {
-    for (int i = tid; i < (C << L); i += nt) {
-      int l = i & ((1 << L) - 1), c = i >> L;
-      if (c < nc) p.dst[(u64)(c0 + c) * p.dst_cs + base + l] = gl::canon(x[l * TP + c]);
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+      if (c < nc) {
+        u64* dp = p.dst + (u64)(c0 + c) * p.dst_cs + base;
+        for (int l = tid; l < (1 << L); l += nt) dp[l] = canon_fast(x[l * TP + c]);
+      }
     }
   } else {
-    for (int i = tid; i < (C << L); i += nt) {
-      int c = i % C, l = i / C;
-      if (c < nc) p.dst[(row0 + base + l) * row_stride + col0 + c0 + c] = gl::canon(x[l * TP + c]);
+    // leaf rows: thread -> (row l0 + k * rows_per_iter, column c): C consecutive threads write one row's C columns
+    const int c = tid % C, l0 = tid / C, rows_per_iter = nt / C;
+    if (c < nc) {
+      u64* dp = p.dst + (row0 + base + l0) * row_stride + col0 + c0 + c;
+      const u64 step = (u64)rows_per_iter * row_stride;
+      for (int l = l0; l < (1 << L); l += rows_per_iter, dp += step) *dp = canon_fast(x[l * TP + c]);
     }
   }
 }
@@ -258,31 +291,20 @@ __global__ void __launch_bounds__(512) intt_final_pass_kernel(PassArgs p, u64 n_
     }
   }
   __syncthreads();
-  // levels: radix-2 groups with per-lane twiddles U[(q_j << a) + lb]
-  for (int a = 0; a < L; a++) {
-    const int ll_bits = L - a - 1;
-    const int items = (1 << (L - 1)) * J;
-    for (int it = tid; it < items; it += nt) {
-      int j = it % J, w = it / J;
-      if (j >= nj) continue;
-      int ll = w & ((1 << ll_bits) - 1), lh = w >> ll_bits;
-      int l0 = (lh << (L - a)) + ll, l1 = l0 + (1 << ll_bits);
-      u64 q = s0 ? (__brevll(qp0 + j) >> (64 - s0)) : 0;
-      u64 z = __ldg(p.U + ((q << a) + lh));
-      u64 u = x[l0 * J + j], v = x[l1 * J + j];
-      gl::Exact exact;
-      butterfly(u, v, z, exact);
-      x[l0 * J + j] = u;
-      x[l1 * J + j] = v;
-    }
-    __syncthreads();
+  // levels: the shared radix-8/4/2 machinery with per-lane twiddles U[(q_j << a) + lb] (lane j = tid % J is fixed
+  // per thread because J divides the block size); exact reductions (the source chunks are re-read nowhere else)
+  {
+    const int j = tid % J;
+    GlobalTwiddles tw{p.U, s0 ? (__brevll(qp0 + min(j, nj - 1)) >> (64 - s0)) : 0};
+    gl::Exact exact;
+    run_levels(x, tw, L, J, J, tid, nt, exact);
   }
   // store: i = rev_L(l) * 2^s0 + q'  -> for fixed l, J consecutive outputs
   for (int i = tid; i < (J << L); i += nt) {
     int j = i % J, l = i / J;
     if (j < nj) {
       u64 hi = L ? (u64)(__brev((u32)l) >> (32 - L)) : 0;
-      dst[(hi << s0) + qp0 + j] = gl::canon(gl::mul(x[l * J + j], n_inv));
+      dst[(hi << s0) + qp0 + j] = canon_fast(gl::mul(x[l * J + j], n_inv));
     }
   }
 }

@@ -286,7 +286,13 @@ extern "C" int p2b_ctx_leaf_hash_time(p2b_ctx* c, double* total_ms, uint64_t* la
 // ======================================================================================================
 // pass planner
 // ======================================================================================================
-static constexpr u32 FINAL_L = 9;      // levels of the last pass (512-row chunks)
+#ifndef P2B_FINAL_L
+#define P2B_FINAL_L 10
+#endif
+#ifndef P2B_STRIDED_T16_MAX_SMEM
+#define P2B_STRIDED_T16_MAX_SMEM (100 * 1024)  // above this a T = 16 tile leaves one CTA per SM: use T = 8
+#endif
+static constexpr u32 FINAL_L = P2B_FINAL_L;  // levels of the last pass (2^FINAL_L-row chunks)
 static constexpr u32 STRIDED_MAX_L = 11;
 static constexpr int FINAL_C = 8;      // columns per CTA in the final LDE / column-major pass
 static constexpr int INTT_J = 16;      // chunks per CTA in the inverse final pass
@@ -320,7 +326,7 @@ static int launch_strided(p2b_ctx* c, cudaStream_t st, const ntt::PassArgs& a, c
   const u64 stride = ((u64)1 << a.k) >> (a.s0 + a.L);
   // T = 16 positions (128-byte segments) unless the tile would not fit in shared memory
   size_t smem16 = ((size_t)(16 + 1) << a.L) * 8;
-  bool use16 = stride >= 16 && smem16 <= c->smem_optin;
+  bool use16 = stride >= 16 && smem16 <= c->smem_optin && smem16 <= (size_t)P2B_STRIDED_T16_MAX_SMEM;
   int T = use16 ? 16 : 8;
   if (stride < (u64)T) return fail(P2B_ERR_INVALID, "internal: strided pass with stride %llu", (unsigned long long)stride);
   size_t smem = ((size_t)(T + 1) << a.L) * 8;
@@ -373,11 +379,18 @@ static int run_ifft(p2b_ctx* c, const u64* src, u64* dst, u64* tmp, u32 k, u64 P
   a.src_cs = a.dst_cs = n;
   a.s0 = pl.final_s0;
   a.L = pl.final_L;
-  size_t smem = ((size_t)INTT_J << a.L) * 8;
-  P2B_TRY(opt_in_smem(ntt::intt_final_pass_kernel<INTT_J>, smem));
   u64 chunks = (u64)1 << a.s0;
-  dim3 grid((unsigned)((chunks + INTT_J - 1) / INTT_J), (unsigned)P);
-  ntt::intt_final_pass_kernel<INTT_J><<<grid, 512, smem, c->stream>>>(a, gl::inverse_2exp(k));
+  if (a.L <= 9) {
+    size_t smem = ((size_t)INTT_J << a.L) * 8;
+    P2B_TRY(opt_in_smem(ntt::intt_final_pass_kernel<INTT_J>, smem));
+    dim3 grid((unsigned)((chunks + INTT_J - 1) / INTT_J), (unsigned)P);
+    ntt::intt_final_pass_kernel<INTT_J><<<grid, 512, smem, c->stream>>>(a, gl::inverse_2exp(k));
+  } else {  // larger chunks: 8 lanes (64-byte output segments) keep the tile at 2^L * 64 bytes
+    size_t smem = ((size_t)8 << a.L) * 8;
+    P2B_TRY(opt_in_smem(ntt::intt_final_pass_kernel<8>, smem));
+    dim3 grid((unsigned)((chunks + 7) / 8), (unsigned)P);
+    ntt::intt_final_pass_kernel<8><<<grid, 512, smem, c->stream>>>(a, gl::inverse_2exp(k));
+  }
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   return P2B_OK;
