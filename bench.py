@@ -36,10 +36,10 @@ RATE_BITS, CAP_HEIGHT = 3, 4
 METRIC = "LDE+Merkle commit ms (2^20x135 cols, rate 3)"
 # dynamic thread-instructions of one Poseidon permutation in the shipped SASS (tools/sass_mix.py / ncu
 # smsp__inst_executed of hash_leaves_kernel divided by permutations; profiles/README.md)
-INSTR_PER_PERM = 24500
+INSTR_PER_PERM = 21830
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE leaf-hash launch (2^20 leaves x 135) from the committed
-# `ncu --set full` capture, profiles/r01_hash_leaves_ncu.md
-HASH_LAUNCH_DRAM_BYTES_2P20_X135 = 1259251000 + 34948096
+# `ncu --set full` capture, profiles/r01b_hash_leaves_ncu.md
+HASH_LAUNCH_DRAM_BYTES_2P20_X135 = 1254320000 + 43090688
 INT_LANES_PER_CLK_PER_SM = 64  # measured IADD3 / IMAD issue rate on B200 (tools/int_peak.cu, profiles/int_peak_r01.md)
 
 
