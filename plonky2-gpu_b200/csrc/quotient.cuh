@@ -74,8 +74,20 @@ __host__ __device__ inline u32 gate_num_constraints(const GateDesc& g) {
   }
 }
 
-// Accumulates sum_j alpha_c^(base + j) * c_j for every challenge; emit() is called in constraint order.
+// Accumulates sum_j alpha_c^(base + j) * c_j for every challenge; emit() is called in constraint order.  M = exact or
+// optimistic field reduction (gl64.cuh): the kernel evaluates a point optimistically and redoes it exactly if `rare`.
+template <class M>
 struct Emitter {
+  M& mode;
+  __device__ __forceinline__ explicit Emitter(M& m) : mode(m) {}
+  __device__ __forceinline__ u64 mul(u64 a, u64 b) { return gl::mul(a, b, mode); }
+  __device__ __forceinline__ u64 mul_add(u64 a, u64 b, u64 c) { return gl::mul_add(a, b, c, mode); }
+  // prod_{x < m} (limb - x)
+  __device__ __forceinline__ u64 range_product(u64 limb, u32 m) {
+    u64 p = limb;
+    for (u32 x = 1; x < m; x++) p = mul(p, gl::sub_canonical(limb, x));
+    return p;
+  }
   u64 acc[MAX_CHALLENGES];
   const u64* ap;  // alpha_pows + base
   u32 stride, nc, j;
@@ -90,54 +102,51 @@ struct Emitter {
   __device__ __forceinline__ void emit(u64 v) {
 #pragma unroll
     for (int c = 0; c < MAX_CHALLENGES; c++)
-      if ((u32)c < nc) acc[c] = gl::mul_add(v, __ldg(ap + (u64)c * stride + j), acc[c]);
+      if ((u32)c < nc) acc[c] = mul_add(v, __ldg(ap + (u64)c * stride + j), acc[c]);
     j++;
   }
 };
 
 __device__ __forceinline__ u64 fsub(u64 a, u64 b) { return gl::sub(a, b); }
 __device__ __forceinline__ u64 fadd(u64 a, u64 b) { return gl::add(a, b); }
-__device__ __forceinline__ u64 fmul(u64 a, u64 b) { return gl::mul(a, b); }
-
-// prod_{x < m} (limb - x)
-__device__ __forceinline__ u64 range_product(u64 limb, u32 m) {
-  u64 p = limb;
-  for (u32 x = 1; x < m; x++) p = fmul(p, fsub(limb, x));
-  return p;
-}
 
 // ---- gates (wires: W[k], constants after the selector prefix: K[k]) ----------------------------------------------
 #define W(k) __ldg(w + (k))
 #define K(k) __ldg(kc + (k))
 
-__device__ __forceinline__ void eval_constant(const GateDesc& g, const u64* w, const u64* kc, Emitter& e) {  // constant.rs:150-158
+template <class M>
+__device__ __forceinline__ void eval_constant(const GateDesc& g, const u64* w, const u64* kc, Emitter<M>& e) {  // constant.rs:150-158
   for (u32 i = 0; i < g.p0; i++) e.emit(fsub(K(i), W(i)));
 }
-__device__ __forceinline__ void eval_public_input(const u64* w, const u64* pih, Emitter& e) {  // public_input.rs:129-139
+template <class M>
+__device__ __forceinline__ void eval_public_input(const u64* w, const u64* pih, Emitter<M>& e) {  // public_input.rs:129-139
   for (u32 i = 0; i < 4; i++) e.emit(fsub(W(i), pih[i]));
 }
-__device__ __forceinline__ void eval_arithmetic(const GateDesc& g, const u64* w, const u64* kc, Emitter& e) {  // arithmetic_base.rs:199-220
+template <class M>
+__device__ __forceinline__ void eval_arithmetic(const GateDesc& g, const u64* w, const u64* kc, Emitter<M>& e) {  // arithmetic_base.rs:199-220
   u64 c0 = K(0), c1 = K(1);
   for (u32 i = 0; i < g.p0; i++) {
-    u64 computed = fadd(fmul(fmul(W(4 * i), W(4 * i + 1)), c0), fmul(W(4 * i + 2), c1));
+    u64 computed = fadd(e.mul(e.mul(W(4 * i), W(4 * i + 1)), c0), e.mul(W(4 * i + 2), c1));
     e.emit(fsub(W(4 * i + 3), computed));
   }
 }
-__device__ __forceinline__ void eval_base_sum(const GateDesc& g, const u64* w, Emitter& e) {  // base_sum.rs:213-230
+template <class M>
+__device__ __forceinline__ void eval_base_sum(const GateDesc& g, const u64* w, Emitter<M>& e) {  // base_sum.rs:213-230
   const u32 nl = g.p0, B = g.p1;
   u64 sum = 0;
-  for (u32 i = nl; i-- > 0;) sum = fadd(fmul(sum, B), W(1 + i));
+  for (u32 i = nl; i-- > 0;) sum = fadd(e.mul(sum, B), W(1 + i));
   e.emit(fsub(sum, W(0)));
-  for (u32 i = 0; i < nl; i++) e.emit(range_product(W(1 + i), B));
+  for (u32 i = 0; i < nl; i++) e.emit(e.range_product(W(1 + i), B));
 }
-__device__ __forceinline__ void eval_random_access(const GateDesc& g, const u64* w, const u64* kc, Emitter& e) {  // random_access.rs:409-450
+template <class M>
+__device__ __forceinline__ void eval_random_access(const GateDesc& g, const u64* w, const u64* kc, Emitter<M>& e) {  // random_access.rs:409-450
   const u32 bits = g.p0, copies = g.p1, extra = g.p2, vs = 1u << g.p0;
   const u32 routed = (2 + vs) * copies + extra;
   for (u32 copy = 0; copy < copies; copy++) {
     const u32 base = (2 + vs) * copy, bbase = routed + copy * bits;
     for (u32 i = 0; i < bits; i++) {
       u64 b = W(bbase + i);
-      e.emit(fmul(b, fsub(b, 1)));
+      e.emit(e.mul(b, fsub(b, 1)));
     }
     u64 acc = 0;
     for (u32 i = bits; i-- > 0;) acc = fadd(fadd(acc, acc), W(bbase + i));
@@ -150,33 +159,35 @@ __device__ __forceinline__ void eval_random_access(const GateDesc& g, const u64*
     for (u32 i = 0; i < bits; i++) {
       u64 b = W(bbase + i);
       len >>= 1;
-      for (u32 k = 0; k < len; k++) items[k] = fadd(items[2 * k], fmul(b, fsub(items[2 * k + 1], items[2 * k])));
+      for (u32 k = 0; k < len; k++) items[k] = fadd(items[2 * k], e.mul(b, fsub(items[2 * k + 1], items[2 * k])));
     }
     e.emit(fsub(items[0], W(base + 1)));
   }
   for (u32 i = 0; i < extra; i++) e.emit(fsub(K(i), W((2 + vs) * copies + i)));
 }
-__device__ __forceinline__ void eval_u32_arithmetic(const GateDesc& g, const u64* w, Emitter& e) {  // arithmetic_u32.rs:326-386
+template <class M>
+__device__ __forceinline__ void eval_u32_arithmetic(const GateDesc& g, const u64* w, Emitter<M>& e) {  // arithmetic_u32.rs:326-386
   const u32 ops = g.p0;
   for (u32 i = 0; i < ops; i++) {
     u64 m0 = W(6 * i), m1 = W(6 * i + 1), add = W(6 * i + 2), lo = W(6 * i + 3), hi = W(6 * i + 4), inverse = W(6 * i + 5);
-    u64 computed = gl::mul_add(m0, m1, add);
+    u64 computed = e.mul_add(m0, m1, add);
     u64 diff = fsub(0xFFFFFFFFull, hi);
-    u64 hi_not_max = fsub(fmul(inverse, diff), 1);
-    e.emit(fmul(hi_not_max, lo));
-    e.emit(fsub(fadd(fmul(hi, 1ull << 32), lo), computed));
+    u64 hi_not_max = fsub(e.mul(inverse, diff), 1);
+    e.emit(e.mul(hi_not_max, lo));
+    e.emit(fsub(fadd(e.mul(hi, 1ull << 32), lo), computed));
     u64 cl = 0, ch = 0;
     for (u32 j = 32; j-- > 0;) {
       u64 limb = W(6 * ops + 32 * i + j);
-      e.emit(range_product(limb, 4));
-      if (j < 16) cl = fadd(fmul(cl, 4), limb);
-      else ch = fadd(fmul(ch, 4), limb);
+      e.emit(e.range_product(limb, 4));
+      if (j < 16) cl = fadd(e.mul(cl, 4), limb);
+      else ch = fadd(e.mul(ch, 4), limb);
     }
     e.emit(fsub(cl, lo));
     e.emit(fsub(ch, hi));
   }
 }
-__device__ __forceinline__ void eval_u32_add_many(const GateDesc& g, const u64* w, Emitter& e) {  // add_many_u32.rs:143-184
+template <class M>
+__device__ __forceinline__ void eval_u32_add_many(const GateDesc& g, const u64* w, Emitter<M>& e) {  // add_many_u32.rs:143-184
   const u32 na = g.p0, ops = g.p1;
   for (u32 i = 0; i < ops; i++) {
     const u32 b = (na + 3) * i;
@@ -184,84 +195,88 @@ __device__ __forceinline__ void eval_u32_add_many(const GateDesc& g, const u64* 
     for (u32 j = 0; j < na; j++) computed = fadd(computed, W(b + j));
     computed = fadd(computed, W(b + na));
     u64 res = W(b + na + 1), oc = W(b + na + 2);
-    e.emit(fsub(fadd(fmul(oc, 1ull << 32), res), computed));
+    e.emit(fsub(fadd(e.mul(oc, 1ull << 32), res), computed));
     u64 cr = 0, cc = 0;
     for (u32 j = 18; j-- > 0;) {
       u64 limb = W((na + 3) * ops + 18 * i + j);
-      e.emit(range_product(limb, 4));
-      if (j < 16) cr = fadd(fmul(cr, 4), limb);
-      else cc = fadd(fmul(cc, 4), limb);
+      e.emit(e.range_product(limb, 4));
+      if (j < 16) cr = fadd(e.mul(cr, 4), limb);
+      else cc = fadd(e.mul(cc, 4), limb);
     }
     e.emit(fsub(cr, res));
     e.emit(fsub(cc, oc));
   }
 }
-__device__ __forceinline__ void eval_u32_range_check(const GateDesc& g, const u64* w, Emitter& e) {  // range_check_u32.rs:89-111
+template <class M>
+__device__ __forceinline__ void eval_u32_range_check(const GateDesc& g, const u64* w, Emitter<M>& e) {  // range_check_u32.rs:89-111
   const u32 n = g.p0;
   for (u32 i = 0; i < n; i++) {
     u64 sum = 0;
-    for (u32 j = 16; j-- > 0;) sum = fadd(fmul(sum, 4), W(n + 16 * i + j));
+    for (u32 j = 16; j-- > 0;) sum = fadd(e.mul(sum, 4), W(n + 16 * i + j));
     e.emit(fsub(sum, W(i)));
-    for (u32 j = 0; j < 16; j++) e.emit(range_product(W(n + 16 * i + j), 4));
+    for (u32 j = 0; j < 16; j++) e.emit(e.range_product(W(n + 16 * i + j), 4));
   }
 }
-__device__ __forceinline__ void eval_u32_subtraction(const GateDesc& g, const u64* w, Emitter& e) {  // subtraction_u32.rs:233-271
+template <class M>
+__device__ __forceinline__ void eval_u32_subtraction(const GateDesc& g, const u64* w, Emitter<M>& e) {  // subtraction_u32.rs:233-271
   const u32 ops = g.p0;
   for (u32 i = 0; i < ops; i++) {
     u64 x = W(5 * i), y = W(5 * i + 1), br = W(5 * i + 2), res = W(5 * i + 3), ob = W(5 * i + 4);
     u64 initial = fsub(fsub(x, y), br);
-    e.emit(fsub(res, fadd(initial, fmul(ob, 1ull << 32))));
+    e.emit(fsub(res, fadd(initial, e.mul(ob, 1ull << 32))));
     u64 comb = 0;
     for (u32 j = 16; j-- > 0;) {
       u64 limb = W(5 * ops + 16 * i + j);
-      e.emit(range_product(limb, 4));
-      comb = fadd(fmul(comb, 4), limb);
+      e.emit(e.range_product(limb, 4));
+      comb = fadd(e.mul(comb, 4), limb);
     }
     e.emit(fsub(comb, res));
-    e.emit(fmul(ob, fsub(1, ob)));
+    e.emit(e.mul(ob, fsub(1, ob)));
   }
 }
-__device__ __forceinline__ void eval_comparison(const GateDesc& g, const u64* w, Emitter& e) {  // comparison.rs:325-402
+template <class M>
+__device__ __forceinline__ void eval_comparison(const GateDesc& g, const u64* w, Emitter<M>& e) {  // comparison.rs:325-402
   const u32 nc = g.p1, cb = (g.p0 + g.p1 - 1) / g.p1;
   u64 fcomb = 0, scomb = 0;
   for (u32 i = nc; i-- > 0;) {
-    fcomb = fadd(fmul(fcomb, 1ull << cb), W(4 + i));
-    scomb = fadd(fmul(scomb, 1ull << cb), W(4 + nc + i));
+    fcomb = fadd(e.mul(fcomb, 1ull << cb), W(4 + i));
+    scomb = fadd(e.mul(scomb, 1ull << cb), W(4 + nc + i));
   }
   e.emit(fsub(fcomb, W(0)));
   e.emit(fsub(scomb, W(1)));
   u64 msd = 0;
   for (u32 i = 0; i < nc; i++) {
     u64 f = W(4 + i), s = W(4 + nc + i);
-    e.emit(range_product(f, 1u << cb));
-    e.emit(range_product(s, 1u << cb));
+    e.emit(e.range_product(f, 1u << cb));
+    e.emit(e.range_product(s, 1u << cb));
     u64 diff = fsub(s, f);
     u64 dummy = W(4 + 2 * nc + i), eq = W(4 + 3 * nc + i), inter = W(4 + 4 * nc + i);
-    e.emit(fsub(fmul(diff, dummy), fsub(1, eq)));
-    e.emit(fmul(eq, diff));
-    e.emit(fsub(inter, fmul(eq, msd)));
-    msd = fadd(inter, fmul(fsub(1, eq), diff));
+    e.emit(fsub(e.mul(diff, dummy), fsub(1, eq)));
+    e.emit(e.mul(eq, diff));
+    e.emit(fsub(inter, e.mul(eq, msd)));
+    msd = fadd(inter, e.mul(fsub(1, eq), diff));
   }
   e.emit(fsub(W(3), msd));
   u64 bits_comb = 0;
   for (u32 i = 0; i <= cb; i++) {
     u64 b = W(4 + 5 * nc + i);
-    e.emit(fmul(b, fsub(1, b)));
+    e.emit(e.mul(b, fsub(1, b)));
   }
   for (u32 i = cb + 1; i-- > 0;) bits_comb = fadd(fadd(bits_comb, bits_comb), W(4 + 5 * nc + i));
   e.emit(fsub(fadd(W(3), 1ull << cb), bits_comb));
   e.emit(fsub(W(2), W(4 + 5 * nc + cb)));
 }
 // gates/poseidon.rs:485-564
-__device__ __forceinline__ void eval_poseidon(const u64* w, Emitter& e) {
+template <class M>
+__device__ __forceinline__ void eval_poseidon(const u64* w, Emitter<M>& e) {
   constexpr u32 SWAP = 24, DELTA = 25, FULL0 = 29, PARTIAL = 29 + 36, FULL1 = 29 + 36 + 22;
   u64 swap = W(SWAP);
-  e.emit(fmul(swap, fsub(swap, 1)));
+  e.emit(e.mul(swap, fsub(swap, 1)));
   u64 s[12];
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     u64 lhs = W(i), rhs = W(i + 4), d = W(DELTA + i);
-    e.emit(fsub(fmul(swap, fsub(rhs, lhs)), d));
+    e.emit(fsub(e.mul(swap, fsub(rhs, lhs)), d));
     s[i] = fadd(lhs, d);
     s[i + 4] = fsub(rhs, d);
   }
@@ -289,16 +304,16 @@ __device__ __forceinline__ void eval_poseidon(const u64* w, Emitter& e) {
         s[8] = v0; s[9] = v1; s[10] = v2; s[11] = v3;
       }
     }
-    sbox_layer(s);
+    sbox_layer(s, e.mode);
     mds_layer(s, &C.post[12 * r]);  // + constants of the next full round / first partial constants after r = 3
   }
-  partial_layer_init(s);
+  partial_layer_init(s, e.mode);
 #pragma unroll 1
   for (int r = 0; r < 22; r++) {
     u64 sbox_in = W(PARTIAL + r);
     e.emit(fsub(s[0], sbox_in));
-    u64 s0 = gl::add_canonical(sbox(sbox_in), C.partial_rc[r]);  // partial_rc[21] == 0 (poseidon.rs:544 adds nothing)
-    partial_layer_fast(s, s0, r);
+    u64 s0 = gl::add_canonical(sbox(sbox_in, e.mode), C.partial_rc[r]);  // partial_rc[21] == 0 (poseidon.rs:544 adds nothing)
+    partial_layer_fast(s, s0, r, e.mode);
   }
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl::add_canonical(s[i], C.rc[12 * 26 + i]);
@@ -317,7 +332,7 @@ __device__ __forceinline__ void eval_poseidon(const u64* w, Emitter& e) {
       for (int i = 0; i < 8; i++) s[i] = s[i + 4];
       s[8] = v0; s[9] = v1; s[10] = v2; s[11] = v3;
     }
-    sbox_layer(s);
+    sbox_layer(s, e.mode);
     mds_layer(s, &C.post[12 * (4 + r)]);
   }
 #pragma unroll 1
@@ -338,10 +353,9 @@ __device__ __forceinline__ void eval_poseidon(const u64* w, Emitter& e) {
 // field inverse by Fermat (the reference uses a binary GCD, field/src/inversion.rs; the value is the same)
 __device__ __forceinline__ u64 finv(u64 a) { return gl::pow(a, gl::P - 2); }
 
-__global__ void __launch_bounds__(128) quotient_values_kernel(Params p) {
-  const u64 lde_size = (u64)1 << (p.degree_bits + p.qdb);
-  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= lde_size) return;
+// All terms of one LDE point folded into acc[c] = sum_t alpha_c^t * term_t (before the division by Z_H).
+template <class M>
+__device__ __forceinline__ void eval_point(const Params& p, const u64 i, const u64 lde_size, M& mode, u64 (&acc)[MAX_CHALLENGES]) {
   const u32 lde_bits = p.degree_bits + p.rate_bits;
   const u32 step_log = p.rate_bits - p.qdb;
   const u64 row = lde_bits ? (__brevll(i << step_log) >> (64 - lde_bits)) : 0;
@@ -353,9 +367,10 @@ __global__ void __launch_bounds__(128) quotient_values_kernel(Params p) {
   const u64* zn = p.zs_pp + row_next * p.zs_stride;
   const u32 nc = p.num_challenges, nr = p.num_routed, npp = p.num_partial_products, md = p.max_degree;
   const u32 rate_mask = (1u << p.qdb) - 1;
+  auto fm = [&](u64 a, u64 b) { return gl::mul(a, b, mode); };
+  auto fma = [&](u64 a, u64 b, u64 c) { return gl::mul_add(a, b, c, mode); };
 
   const u64 x = gl::mul(7, gl::pow(p.w, i));  // shifted_x = coset_shift * w^i (prover.rs:907)
-  u64 acc[MAX_CHALLENGES];
 #pragma unroll
   for (int c = 0; c < MAX_CHALLENGES; c++) acc[c] = 0;
 
@@ -368,23 +383,23 @@ __global__ void __launch_bounds__(128) quotient_values_kernel(Params p) {
     const u32 chunks = npp + 1;
     for (u32 tc = 0; tc < nc; tc++) {
       const u64 z_x = __ldg(zp + tc), z_gx = __ldg(zn + tc);
-      const u64 t_z1 = gl::mul(l0, gl::sub(z_x, 1));
-      for (u32 c = 0; c < nc; c++) acc[c] = gl::mul_add(t_z1, __ldg(p.alpha_pows + (u64)c * p.num_terms + tc), acc[c]);
+      const u64 t_z1 = fm(l0, gl::sub(z_x, 1));
+      for (u32 c = 0; c < nc; c++) acc[c] = fma(t_z1, __ldg(p.alpha_pows + (u64)c * p.num_terms + tc), acc[c]);
       const u64 beta = p.betas[tc], gamma = p.gammas[tc];
-      const u64 bx = gl::mul(beta, x);
+      const u64 bx = fm(beta, x);
       u64 prev = z_x;
       for (u32 ch = 0; ch < chunks; ch++) {
         u64 num = 1, den = 1;
         const u32 j1 = min(nr, (ch + 1) * md);
         for (u32 j = ch * md; j < j1; j++) {
           const u64 wv = __ldg(w + j);
-          num = gl::mul(num, gl::add(gl::add(wv, gl::mul(bx, __ldg(p.k_is + j))), gamma));               // :175-181
-          den = gl::mul(den, gl::add(gl::add(wv, gl::mul(beta, __ldg(cs + p.num_constants + j))), gamma));  // :182-186
+          num = fm(num, gl::add(gl::add(wv, fm(bx, __ldg(p.k_is + j))), gamma));                    // :175-181
+          den = fm(den, gl::add(gl::add(wv, fm(beta, __ldg(cs + p.num_constants + j))), gamma));     // :182-186
         }
         const u64 next = ch + 1 < chunks ? __ldg(zp + nc + tc * npp + ch) : z_gx;
-        const u64 term = gl::sub(gl::mul(prev, num), gl::mul(next, den));  // partial_products.rs:70-75
+        const u64 term = gl::sub(fm(prev, num), fm(next, den));  // partial_products.rs:70-75
         for (u32 c = 0; c < nc; c++)
-          acc[c] = gl::mul_add(term, __ldg(p.alpha_pows + (u64)c * p.num_terms + nc + tc * chunks + ch), acc[c]);
+          acc[c] = fma(term, __ldg(p.alpha_pows + (u64)c * p.num_terms + nc + tc * chunks + ch), acc[c]);
         prev = next;
       }
     }
@@ -399,9 +414,9 @@ __global__ void __launch_bounds__(128) quotient_values_kernel(Params p) {
     const u64 s = __ldg(cs + g.selector_index);
     u64 filter = 1;
     for (u32 k = g.group_start; k < g.group_end; k++)
-      if (k != gi) filter = gl::mul(filter, gl::sub((u64)k, s));
-    if (p.num_selectors > 1) filter = gl::mul(filter, gl::sub(0xFFFFFFFFull, s));
-    Emitter e;
+      if (k != gi) filter = fm(filter, gl::sub((u64)k, s));
+    if (p.num_selectors > 1) filter = fm(filter, gl::sub(0xFFFFFFFFull, s));
+    Emitter<M> e(mode);
     e.init(p.alpha_pows, p.num_terms, gate_base, nc);
     switch (g.type) {
       case G_NOOP: break;
@@ -420,11 +435,27 @@ __global__ void __launch_bounds__(128) quotient_values_kernel(Params p) {
     }
 #pragma unroll
     for (int c = 0; c < MAX_CHALLENGES; c++)
-      if ((u32)c < nc) acc[c] = gl::mul_add(filter, e.acc[c], acc[c]);
+      if ((u32)c < nc) acc[c] = fma(filter, e.acc[c], acc[c]);
   }
+}
 
+__global__ void __launch_bounds__(128) quotient_values_kernel(Params p) {
+  const u64 lde_size = (u64)1 << (p.degree_bits + p.qdb);
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= lde_size) return;
+  u64 acc[MAX_CHALLENGES];
+#ifndef P2B_EXACT_ONLY
+  gl::Optimistic fast;
+  eval_point(p, i, lde_size, fast, acc);
+  if (fast.rare)  // an optimistic reduction hit its rare case somewhere in this point: redo the point exactly
+#endif
+  {
+    gl::Exact exact;
+    eval_point(p, i, lde_size, exact, acc);
+  }
   // ---- divide by Z_H (prover.rs:985-991) ----
-  const u64 zi = p.zh_inv[i & rate_mask];
+  const u32 nc = p.num_challenges;
+  const u64 zi = p.zh_inv[i & ((1u << p.qdb) - 1)];
 #pragma unroll
   for (int c = 0; c < MAX_CHALLENGES; c++) {
     if ((u32)c < nc) {
