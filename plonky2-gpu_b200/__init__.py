@@ -334,6 +334,21 @@ def compute_quotient_polys(ctx, circuit, wires, zs_partial_products, constants_s
     return dv.to_host().reshape(nc, size), dc.to_host().reshape(nc, size)
 
 
+def compute_quotient_polys_rows(ctx, circuit, wires_rows, zs_pp_rows, consts_sigmas_rows, public_inputs_hash, betas, gammas, alphas):
+    """Same as compute_quotient_polys, on raw LDE rows ([lde_size][width] uint64, bit-reversed row order) instead of committed
+    batches -- the shape the reference kernel reads (plonky2_gpu.cu:684-760: d_ext_wires / d_ext_zs / d_ext_constants_sigmas)."""
+    nc, size = circuit.num_challenges, circuit.lde_size
+    mats = [np.ascontiguousarray(m, dtype=np.uint64) for m in (wires_rows, zs_pp_rows, consts_sigmas_rows)]
+    devs = [DeviceBuffer.from_host(ctx, m.reshape(-1)) for m in mats]
+    dv, dc = DeviceBuffer(ctx, nc * size), DeviceBuffer(ctx, nc * size)
+    arr = lambda x, n: (C.c_uint64 * n)(*[int(v) % ORDER for v in x])
+    _check(lib().p2b_quotient_polys_rows(ctx.handle, C.byref(circuit.struct), devs[0].ptr, mats[0].shape[1], devs[1].ptr, mats[1].shape[1],
+                                         devs[2].ptr, mats[2].shape[1], arr(public_inputs_hash, 4), arr(betas, nc), arr(gammas, nc),
+                                         arr(alphas, nc), dv.ptr, dc.ptr))
+    ctx.synchronize()
+    return dv.to_host().reshape(nc, size), dc.to_host().reshape(nc, size)
+
+
 class MerkleTree:
     """View of a committed batch's tree (reference: MerkleTree {leaves, digests, cap}, merkle_tree.rs:41-66)."""
 

@@ -67,6 +67,32 @@ def test_quotient_random_data_matches_oracle(ctx):
         assert np.array_equal(coeffs[c], ecoeffs[c])
 
 
+def test_quotient_edge_values_take_the_exact_redo_path(ctx):
+    # raw LDE rows filled with the operands that make the optimistic reduction flag its rare case (2^48 * 2^48 = 2^96,
+    # eps * eps, (p-1)^2 ...): those points are recomputed by the exact path and must still be bit-identical
+    gates, groups, sel = F.standard_gate_sets()[1]
+    inst = F.build_instance(gates, groups, sel, 3, 135, 80, seed=71)
+    c = inst.circ
+    N = c.lde_size if hasattr(c, "lde_size") else 1 << (c.degree_bits + c.rate_bits)
+    edge = np.array([0, 1, 2, P - 1, P - 2, 2**32 - 1, 2**32, 2**32 + 1, 2**48, 2**48 - 1, 2**48 + 1, 2**63, P - 2**32,
+                     P - 2**48, 2**64 - 2**33, 2**16, 2**47, 2**49], dtype=np.uint64)
+    rng = np.random.default_rng(72)
+    mats = []
+    for m in (inst.wires, inst.zs_pp, inst.consts_sigmas):
+        r = rng.integers(0, P, size=(N, m.shape[0]), dtype=np.uint64)
+        pick = rng.integers(0, 2, size=r.shape).astype(bool)
+        r[pick] = edge[rng.integers(0, edge.size, size=int(pick.sum()))]
+        mats.append(r)
+    # keep the selector columns meaningful so that every gate's evaluator runs on some rows
+    mats[2][:, :c.num_selectors] = rng.integers(0, len(gates), size=(N, c.num_selectors), dtype=np.uint64)
+    challenges = [2**48, P - 1], [2**32 - 1, 2**48], [2**48, 2**48 + 1]
+    vals, coeffs = p2b.compute_quotient_polys_rows(ctx, to_p2b_circuit(c), *mats, inst.pih, *challenges)
+    evals, ecoeffs = Q.compute_quotient_polys(c, *mats, inst.pih, *challenges)
+    for ch in range(c.num_challenges):
+        assert np.array_equal(vals[ch], evals[ch])
+        assert np.array_equal(coeffs[ch], ecoeffs[ch])
+
+
 @pytest.mark.parametrize("num_wires,num_routed,nch,qdf,rate_bits", [(136, 80, 2, 8, 3), (234, 80, 2, 8, 3), (40, 12, 3, 4, 2), (60, 9, 1, 8, 3)])
 def test_quotient_other_configs(ctx, num_wires, num_routed, nch, qdf, rate_bits):
     # standard_ecc_config (136 wires), wide_ecc_config (234 wires) and odd shapes (routed wires not a multiple of the
