@@ -195,6 +195,7 @@ class Batch:
 
     def __init__(self, coeffs, leaves, digests, cap, n_log, rate_bits, salt_size):
         self.coeffs, self.leaves, self.digests, self.cap = coeffs, leaves, digests, cap
+        self.cap_height = int(cap.shape[0]).bit_length() - 1
         self.degree_log, self.rate_bits, self.salt_size = n_log, rate_bits, salt_size
 
     def get_lde_values(self, index, step=1):
