@@ -191,6 +191,69 @@ int p2b_quotient_polys_rows(p2b_ctx* ctx, const p2b_circuit* circuit, const uint
                             const uint64_t* gammas, const uint64_t* alphas, uint64_t* d_values_out, uint64_t* d_coeffs_out);
 
 /* ---------------------------------------------------------------------------------------------------
+ * FRI opening proof (SURVEY.md section 8(f) rank 1 + 4): PolynomialBatch::prove_openings (plonky2/src/fri/oracle.rs:1046-1110)
+ * -> fri_proof (plonky2/src/fri/prover.rs:23-70), and OpeningSet::new's evaluations (plonky2/src/plonk/proof.rs:305-334).
+ * The reference runs all of it on the CPU; here the committed batches never leave the device:
+ *   alpha <- challenger; final_poly = X * sum_i alpha^(k_i) (F_i - F_i(z_i)) / (X - z_i), F_i = sum_j alpha^j f_ij
+ *   (reduce_polys_base + divide_by_linear + shift_poly, util/reducing.rs:87-111, field/src/polynomial/division.rs:75-88);
+ *   coset LDE over the quadratic extension; per reduction: Merkle tree over arity-sized bit-reversed chunks, observe_cap,
+ *   beta, fold the coefficients, coset FFT on shift^arity (prover.rs:76-120); final polynomial; proof-of-work grinding
+ *   (prover.rs:123-171); query indices and the rows + Merkle paths of every tree (prover.rs:173-260).
+ * Extension elements are pairs (c0, c1) of F[X]/(X^2 - 7) (field/src/goldilocks_extensions.rs:14-28).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct {
+  uint64_t sponge_state[12]; /* iop/challenger.rs:16-21 */
+  uint64_t input_buffer[8];
+  uint64_t output_buffer[8]; /* challenges are popped from the END (Vec::pop, challenger.rs:90-92) */
+  uint32_t input_len, output_len;
+} p2b_challenger;
+typedef struct {
+  uint32_t oracle_index, polynomial_index; /* FriPolynomialInfo, fri/structure.rs:46-52 */
+} p2b_fri_poly_info;
+typedef struct {
+  uint64_t point[2];                     /* FriBatchInfo.point, fri/structure.rs:34-38 */
+  const p2b_fri_poly_info* polynomials;  /* host */
+  uint32_t num_polynomials, reserved;
+} p2b_fri_batch_info;
+typedef struct {
+  uint32_t degree_bits, rate_bits, cap_height, proof_of_work_bits, num_query_rounds; /* FriParams / FriConfig, fri/mod.rs:17-75 */
+  uint32_t num_reductions;
+  const uint32_t* reduction_arity_bits;  /* host [num_reductions] */
+} p2b_fri_params;
+typedef struct {
+  uint32_t num_reductions, num_query_rounds, num_oracles, cap_height;
+  uint64_t final_poly_len;  /* extension elements */
+  uint64_t lde_size;
+} p2b_fri_proof_info;
+typedef struct p2b_fri_proof p2b_fri_proof;
+
+/* f(point) for every polynomial of a committed batch (eval_commitment, proof.rs:313-319); out: host [num_polys][2]. */
+int p2b_eval_openings(p2b_ctx* ctx, const p2b_batch* batch, const uint64_t point[2], uint64_t* out);
+/* prove_openings.  `challenger` (host) is the transcript state on entry and is advanced exactly as the reference advances
+ * it (alpha, caps/betas, final polynomial, PoW witness + response, query challenges).  Oracles must be whole (unsharded)
+ * batches of the same degree with rate_bits == params->rate_bits. */
+int p2b_fri_prove_openings(p2b_ctx* ctx, const p2b_batch* const* oracles, uint32_t num_oracles,
+                           const p2b_fri_batch_info* batches, uint32_t num_batches, p2b_challenger* challenger,
+                           const p2b_fri_params* params, p2b_fri_proof** out);
+void p2b_fri_proof_destroy(p2b_fri_proof* proof);
+int p2b_fri_proof_get_info(const p2b_fri_proof* proof, p2b_fri_proof_info* out);
+/* commit_phase_merkle_caps[round]: [2^cap_height][4] */
+int p2b_fri_proof_get_cap(const p2b_fri_proof* proof, uint32_t round, uint64_t* out);
+int p2b_fri_proof_get_final_poly(const p2b_fri_proof* proof, uint64_t* out /* [final_poly_len][2] */);
+int p2b_fri_proof_get_pow_witness(const p2b_fri_proof* proof, uint64_t* out);
+int p2b_fri_proof_get_query_indices(const p2b_fri_proof* proof, uint64_t* out /* [num_query_rounds] */);
+/* FriInitialTreeProof of every query for one oracle: rows [Q][leaf_len] (salt columns included, as MerkleTree::get returns
+ * them), siblings [Q][lde_bits - cap_height][4]. */
+int p2b_fri_proof_get_initial(const p2b_fri_proof* proof, uint32_t oracle, uint64_t* rows_out, uint64_t* siblings_out);
+/* FriQueryStep of every query for one reduction: evals [Q][arity][2], siblings [Q][depth][4];
+ * depth = log2(tree leaves) - cap_height is returned in *depth_out when non-NULL (either output may be NULL). */
+int p2b_fri_proof_get_step(const p2b_fri_proof* proof, uint32_t round, uint64_t* evals_out, uint64_t* siblings_out,
+                           uint32_t* depth_out);
+/* Transcript values, for parity tests: what = 0 alpha [2], 1 betas [num_reductions][2], 2 the polynomial that enters FRI
+ * (oracle.rs:1084) [n][2], 3 PoW response [1]. */
+int p2b_fri_proof_get_debug(const p2b_fri_proof* proof, uint32_t what, uint64_t* out);
+
+/* ---------------------------------------------------------------------------------------------------
  * Building blocks (device pointers unless stated).  Each mirrors one reference function.
  * ------------------------------------------------------------------------------------------------- */
 /* values.into_par_iter().map(|v| v.ifft())  (fri/oracle.rs:717-721, field/src/fft.rs:73-103).

@@ -65,6 +65,32 @@ class CircuitStruct(C.Structure):
                 ("gates", C.POINTER(Gate)), ("k_is", C.POINTER(C.c_uint64))]
 
 
+class ChallengerStruct(C.Structure):
+    """p2b_challenger == Challenger {sponge_state, input_buffer, output_buffer} (iop/challenger.rs:15-21)."""
+    _fields_ = [("sponge_state", C.c_uint64 * 12), ("input_buffer", C.c_uint64 * 8), ("output_buffer", C.c_uint64 * 8),
+                ("input_len", C.c_uint32), ("output_len", C.c_uint32)]
+
+
+class FriPolyInfo(C.Structure):
+    _fields_ = [("oracle_index", C.c_uint32), ("polynomial_index", C.c_uint32)]
+
+
+class FriBatchInfoStruct(C.Structure):
+    _fields_ = [("point", C.c_uint64 * 2), ("polynomials", C.POINTER(FriPolyInfo)), ("num_polynomials", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+class FriParamsStruct(C.Structure):
+    _fields_ = [("degree_bits", C.c_uint32), ("rate_bits", C.c_uint32), ("cap_height", C.c_uint32),
+                ("proof_of_work_bits", C.c_uint32), ("num_query_rounds", C.c_uint32), ("num_reductions", C.c_uint32),
+                ("reduction_arity_bits", C.POINTER(C.c_uint32))]
+
+
+class FriProofInfo(C.Structure):
+    _fields_ = [("num_reductions", C.c_uint32), ("num_query_rounds", C.c_uint32), ("num_oracles", C.c_uint32),
+                ("cap_height", C.c_uint32), ("final_poly_len", C.c_uint64), ("lde_size", C.c_uint64)]
+
+
 GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_BASE_SUM, GATE_POSEIDON, GATE_RANDOM_ACCESS = range(7)
 GATE_U32_ARITHMETIC, GATE_U32_ADD_MANY, GATE_U32_RANGE_CHECK, GATE_U32_SUBTRACTION, GATE_COMPARISON = range(7, 12)
 
@@ -138,6 +164,18 @@ def lib():
         "p2b_batch_finish_layers": (i, [vp, u32]),
         "p2b_quotient_polys": (i, [vp, C.POINTER(CircuitStruct), vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "p2b_quotient_polys_rows": (i, [vp, C.POINTER(CircuitStruct), vp, u64, vp, u64, vp, u64, vp, vp, vp, vp, vp, vp]),
+        "p2b_eval_openings": (i, [vp, vp, vp, vp]),
+        "p2b_fri_prove_openings": (i, [vp, vp, u32, C.POINTER(FriBatchInfoStruct), u32, C.POINTER(ChallengerStruct),
+                                       C.POINTER(FriParamsStruct), C.POINTER(vp)]),
+        "p2b_fri_proof_destroy": (None, [vp]),
+        "p2b_fri_proof_get_info": (i, [vp, C.POINTER(FriProofInfo)]),
+        "p2b_fri_proof_get_cap": (i, [vp, u32, vp]),
+        "p2b_fri_proof_get_final_poly": (i, [vp, vp]),
+        "p2b_fri_proof_get_pow_witness": (i, [vp, vp]),
+        "p2b_fri_proof_get_query_indices": (i, [vp, vp]),
+        "p2b_fri_proof_get_initial": (i, [vp, u32, vp, vp]),
+        "p2b_fri_proof_get_step": (i, [vp, u32, vp, vp, C.POINTER(u32)]),
+        "p2b_fri_proof_get_debug": (i, [vp, u32, vp]),
         "p2b_ifft_batch": (i, [vp, vp, vp, u32, u64]),
         "p2b_lde_leaves": (i, [vp, vp, u32, u64, u32, vp, u64, u64]),
         "p2b_merkle_tree": (i, [vp, vp, u64, u64, u64, u64, u32, vp, vp]),
@@ -347,6 +385,115 @@ def compute_quotient_polys_rows(ctx, circuit, wires_rows, zs_pp_rows, consts_sig
                                          arr(alphas, nc), dv.ptr, dc.ptr))
     ctx.synchronize()
     return dv.to_host().reshape(nc, size), dc.to_host().reshape(nc, size)
+
+
+class Challenger:
+    """Host view of the transcript state the FRI calls advance (iop/challenger.rs:15-150).  Only the state lives here:
+    permutations run on the device inside p2b_fri_prove_openings."""
+
+    def __init__(self, sponge_state=None, input_buffer=(), output_buffer=()):
+        self.struct = ChallengerStruct()
+        for k, v in enumerate(sponge_state if sponge_state is not None else [0] * 12):
+            self.struct.sponge_state[k] = int(v) % ORDER
+        for k, v in enumerate(input_buffer):
+            self.struct.input_buffer[k] = int(v) % ORDER
+        for k, v in enumerate(output_buffer):
+            self.struct.output_buffer[k] = int(v) % ORDER
+        self.struct.input_len, self.struct.output_len = len(input_buffer), len(output_buffer)
+
+    @property
+    def sponge_state(self):
+        return [int(x) for x in self.struct.sponge_state]
+
+    @property
+    def input_buffer(self):
+        return [int(x) for x in self.struct.input_buffer][:self.struct.input_len]
+
+    @property
+    def output_buffer(self):
+        return [int(x) for x in self.struct.output_buffer][:self.struct.output_len]
+
+
+class FriProof:
+    """FriProof (fri/proof.rs) as produced by p2b_fri_prove_openings; arrays are numpy uint64."""
+
+    def __init__(self, handle, arity_bits, oracle_leaf_lens, oracle_depths):
+        self.handle = handle
+        self.arity_bits = list(arity_bits)
+        info = FriProofInfo()
+        _check(lib().p2b_fri_proof_get_info(handle, C.byref(info)))
+        self.info = info
+        R, Q, ncap = info.num_reductions, info.num_query_rounds, 1 << info.cap_height
+        L = lib()
+        get = lambda fn, shape, *a: (lambda arr: (_check(fn(handle, *a, arr.ctypes.data_as(C.c_void_p))), arr)[1])(
+            np.zeros(shape, dtype=np.uint64))
+        self.commit_phase_merkle_caps = [get(L.p2b_fri_proof_get_cap, (ncap, 4), r) for r in range(R)]
+        self.final_poly = get(L.p2b_fri_proof_get_final_poly, (info.final_poly_len, 2))
+        self.pow_witness = int(get(L.p2b_fri_proof_get_pow_witness, (1,))[0])
+        self.query_indices = [int(x) for x in get(L.p2b_fri_proof_get_query_indices, (max(Q, 1),))[:Q]]
+        self.alpha = tuple(int(x) for x in get(L.p2b_fri_proof_get_debug, (2,), 0))
+        self.betas = [tuple(int(x) for x in b) for b in get(L.p2b_fri_proof_get_debug, (max(R, 1), 2), 1)[:R]]
+        self.pow_response = int(get(L.p2b_fri_proof_get_debug, (1,), 3)[0])
+        self.initial = []   # per oracle: (rows [Q][leaf_len], siblings [Q][depth][4])
+        for o, (ll, d) in enumerate(zip(oracle_leaf_lens, oracle_depths)):
+            rows, sibs = np.zeros((Q, ll), dtype=np.uint64), np.zeros((Q, d, 4), dtype=np.uint64)
+            _check(L.p2b_fri_proof_get_initial(handle, o, rows.ctypes.data_as(C.c_void_p), sibs.ctypes.data_as(C.c_void_p)))
+            self.initial.append((rows, sibs))
+        self.steps = []     # per reduction: (evals [Q][arity][2], siblings [Q][depth][4])
+        for r in range(R):
+            depth = C.c_uint32()
+            _check(L.p2b_fri_proof_get_step(handle, r, None, None, C.byref(depth)))
+            ev, sibs = np.zeros((Q, 1 << self.arity_bits[r], 2), dtype=np.uint64), np.zeros((Q, depth.value, 4), dtype=np.uint64)
+            _check(L.p2b_fri_proof_get_step(handle, r, ev.ctypes.data_as(C.c_void_p), sibs.ctypes.data_as(C.c_void_p), None))
+            self.steps.append((ev, sibs))
+
+    def final_poly_in(self, n):
+        """The polynomial that enters FRI (fri/oracle.rs:1084), [n][2] -- parity-test accessor."""
+        out = np.zeros((n, 2), dtype=np.uint64)
+        _check(lib().p2b_fri_proof_get_debug(self.handle, 2, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def close(self):
+        if self.handle:
+            lib().p2b_fri_proof_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def eval_openings(ctx, batch, point):
+    """eval_commitment of OpeningSet::new (plonk/proof.rs:313-319): [num_polys][2]."""
+    out = np.zeros((batch.num_polys, 2), dtype=np.uint64)
+    pt = (C.c_uint64 * 2)(int(point[0]) % ORDER, int(point[1]) % ORDER)
+    _check(lib().p2b_eval_openings(ctx.handle, batch.handle, pt, out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def fri_prove_openings(ctx, oracles, batches, challenger, degree_bits, rate_bits, cap_height, proof_of_work_bits,
+                       num_query_rounds, reduction_arity_bits):
+    """PolynomialBatch::prove_openings (fri/oracle.rs:1046-1110).  oracles: PolynomialBatch list; batches: list of
+    (point (c0, c1), [(oracle_index, polynomial_index), ...]); challenger: Challenger (advanced in place)."""
+    keep = []
+    bstructs = (FriBatchInfoStruct * max(len(batches), 1))()
+    for k, (point, polys) in enumerate(batches):
+        arr = (FriPolyInfo * max(len(polys), 1))()
+        for j, (o, p) in enumerate(polys):
+            arr[j].oracle_index, arr[j].polynomial_index = o, p
+        keep.append(arr)
+        bstructs[k].point[0], bstructs[k].point[1] = int(point[0]) % ORDER, int(point[1]) % ORDER
+        bstructs[k].polynomials, bstructs[k].num_polynomials = arr, len(polys)
+    ab = (C.c_uint32 * max(len(reduction_arity_bits), 1))(*reduction_arity_bits)
+    params = FriParamsStruct(degree_bits, rate_bits, cap_height, proof_of_work_bits, num_query_rounds, len(reduction_arity_bits), ab)
+    handles = (C.c_void_p * max(len(oracles), 1))(*[o.handle for o in oracles])
+    out = C.c_void_p()
+    _check(lib().p2b_fri_prove_openings(ctx.handle, handles, len(oracles), bstructs, len(batches), C.byref(challenger.struct),
+                                        C.byref(params), C.byref(out)))
+    return FriProof(out, reduction_arity_bits, [o.leaf_len for o in oracles],
+                    [o.degree_log + o.rate_bits - o.cap_height for o in oracles])
 
 
 class MerkleTree:

@@ -21,6 +21,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <algorithm>
 #include <new>
 #include <string>
 #include <vector>
@@ -29,6 +30,7 @@
 #include "merkle.cuh"
 #include "ntt.cuh"
 #include "quotient.cuh"
+#include "fri.cuh"
 
 using gl::u32;
 using gl::u64;
@@ -396,10 +398,10 @@ static int run_ifft(p2b_ctx* c, const u64* src, u64* dst, u64* tmp, u32 k, u64 P
   return P2B_OK;
 }
 
-// sigma[s] = g^(n / 2^(s+1)) for the LDE sub-problem of size n = 2^k
-static ntt::LevelScale lde_scale(u32 k) {
+// sigma[s] = shift^(n / 2^(s+1)) for the LDE sub-problem of size n = 2^k on the coset shift * H
+static ntt::LevelScale lde_scale(u32 k, u64 shift = hostf::COSET_SHIFT) {
   ntt::LevelScale sc{};
-  for (u32 s = 0; s < k; s++) sc.sigma[s] = hostf::pow(hostf::COSET_SHIFT, ((u64)1 << k) >> (s + 1));
+  for (u32 s = 0; s < k; s++) sc.sigma[s] = hostf::pow(shift, ((u64)1 << k) >> (s + 1));
   return sc;
 }
 
@@ -1169,4 +1171,5 @@ extern "C" int p2b_quotient_polys(p2b_ctx* ctx, const p2b_circuit* circuit, cons
                        consts_sigmas->info.leaf_len, public_inputs_hash, betas, gammas, alphas, d_values_out, d_coeffs_out, nullptr);
 }
 
+#include "fri_api.cuh"
 #include "compat.cuh"
