@@ -191,6 +191,22 @@ int p2b_quotient_polys_rows(p2b_ctx* ctx, const p2b_circuit* circuit, const uint
                             const uint64_t* gammas, const uint64_t* alphas, uint64_t* d_values_out, uint64_t* d_coeffs_out);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Permutation argument: all_wires_permutation_partial_products (plonky2/src/plonk/prover.rs:702-786)
+ * followed by the re-ordering of prover.rs:112-117, i.e. the matrix the reference commits as zs_partial_products.
+ *   d_wires_values  column-major [>= num_routed_wires][n]: the witness (MatrixWitness.wire_values, iop/witness.rs)
+ *   d_sigma_values  column-major [num_routed_wires][n]: values of the sigma polynomials on H (prover_data.sigmas, transposed)
+ *   k_is, betas, gammas: host arrays ([num_routed_wires], [num_challenges], [num_challenges])
+ *   d_out           column-major [num_challenges * ceil(num_routed_wires / quotient_degree_factor)][n]:
+ *                   Z_c for every challenge, then the partial products of challenge 0, 1, ... (canonical values)
+ * A zero denominator (probability ~ n * num_routed / p for honest challenges) yields zeros where the reference's
+ * batch_multiplicative_inverse would panic.
+ * ------------------------------------------------------------------------------------------------- */
+int p2b_partial_products_and_zs(p2b_ctx* ctx, const uint64_t* d_wires_values, const uint64_t* d_sigma_values,
+                                uint32_t degree_bits, uint32_t num_routed_wires, uint32_t quotient_degree_factor,
+                                uint32_t num_challenges, const uint64_t* k_is, const uint64_t* betas, const uint64_t* gammas,
+                                uint64_t* d_out);
+
+/* ---------------------------------------------------------------------------------------------------
  * FRI opening proof (SURVEY.md section 8(f) rank 1 + 4): PolynomialBatch::prove_openings (plonky2/src/fri/oracle.rs:1046-1110)
  * -> fri_proof (plonky2/src/fri/prover.rs:23-70), and OpeningSet::new's evaluations (plonky2/src/plonk/proof.rs:305-334).
  * The reference runs all of it on the CPU; here the committed batches never leave the device:

@@ -539,6 +539,42 @@ def check_partial_products(nums, dens, partials, z_x, z_gx, max_degree):
     return out
 
 
+def wires_permutation_partial_products_and_zs(wires_values, sigma_values, k_is, beta, gamma, max_degree, degree_bits):
+    """plonk/prover.rs:729-786 for one challenge.  wires_values [num_wires][n], sigma_values [num_routed][n] (values on H,
+    row i at x = w^i).  Returns [num_partial_products + 1][n]: the partial-product polynomials, then Z LAST (the caller
+    pops it to the front, prover.rs:112-117)."""
+    n = 1 << degree_bits
+    nr = len(k_is)
+    w = root_of_unity(degree_bits)
+    x, z_x, rows = 1, 1, []
+    for i in range(n):
+        nums = [(int(wires_values[j][i]) + beta * (k_is[j] * x % P) + gamma) % P for j in range(nr)]
+        dens = [(int(wires_values[j][i]) + beta * int(sigma_values[j][i]) + gamma) % P for j in range(nr)]
+        quot = [a * inv(b) % P for a, b in zip(nums, dens)]       # batch_multiplicative_inverse + mul, :757-761
+        chunk = []                                               # quotient_chunk_products, partial_products.rs:13-24
+        for c in range(0, nr, max_degree):
+            v = 1
+            for q in quot[c:c + max_degree]:
+                v = v * q % P
+            chunk.append(v)
+        acc, res = z_x, []                                       # partial_products_and_z_gx, :28-37
+        for v in chunk:
+            acc = acc * v % P
+            res.append(acc)
+        z_x, res[-1] = res[-1], z_x                              # swap(&mut z_x, &mut res[num_prods]), :778
+        rows.append(res)
+        x = x * w % P
+    return [[rows[i][k] for i in range(n)] for k in range(len(rows[0]))]   # transpose
+
+
+def all_zs_partial_products(wires_values, sigma_values, k_is, betas, gammas, max_degree, degree_bits):
+    """prover.rs:106-117: the matrix committed as zs_partial_products: [Z_c for c] + [pp_{c,k} for c for k]."""
+    per = [wires_permutation_partial_products_and_zs(wires_values, sigma_values, k_is, b, g, max_degree, degree_bits)
+           for b, g in zip(betas, gammas)]
+    zs = [pp.pop() for pp in per]
+    return zs + [col for pp in per for col in pp]
+
+
 def root_of_unity(k):
     b = 1753635133440165772
     for _ in range(32 - k):

@@ -164,6 +164,7 @@ def lib():
         "p2b_batch_finish_layers": (i, [vp, u32]),
         "p2b_quotient_polys": (i, [vp, C.POINTER(CircuitStruct), vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "p2b_quotient_polys_rows": (i, [vp, C.POINTER(CircuitStruct), vp, u64, vp, u64, vp, u64, vp, vp, vp, vp, vp, vp]),
+        "p2b_partial_products_and_zs": (i, [vp, vp, vp, u32, u32, u32, u32, vp, vp, vp, vp]),
         "p2b_eval_openings": (i, [vp, vp, vp, vp]),
         "p2b_fri_prove_openings": (i, [vp, vp, u32, C.POINTER(FriBatchInfoStruct), u32, C.POINTER(ChallengerStruct),
                                        C.POINTER(FriParamsStruct), C.POINTER(vp)]),
@@ -385,6 +386,26 @@ def compute_quotient_polys_rows(ctx, circuit, wires_rows, zs_pp_rows, consts_sig
                                          arr(alphas, nc), dv.ptr, dc.ptr))
     ctx.synchronize()
     return dv.to_host().reshape(nc, size), dc.to_host().reshape(nc, size)
+
+
+def partial_products_and_zs(ctx, wires_values, sigma_values, k_is, betas, gammas, quotient_degree_factor):
+    """all_wires_permutation_partial_products + the Z-first ordering (plonk/prover.rs:702-786, :112-117).
+    wires_values [num_wires][n], sigma_values [num_routed][n]: numpy arrays or (DeviceBuffer, rows, n).
+    Returns a DeviceBuffer holding [num_challenges * ceil(num_routed / qdf)][n] and its shape."""
+    def dev(x):
+        if isinstance(x, tuple):
+            return x
+        x = _np(x)
+        return DeviceBuffer.from_host(ctx, x.reshape(-1)), x.shape[0], x.shape[1]
+    (dw, _, n), (ds, nr, n2) = dev(wires_values), dev(sigma_values)
+    assert n == n2 and nr == len(k_is)
+    nc = len(betas)
+    K = -(-nr // quotient_degree_factor)
+    out = DeviceBuffer(ctx, max(nc * K, 1) * n)
+    arr = lambda x: (C.c_uint64 * max(len(x), 1))(*[int(v) % ORDER for v in x])
+    _check(lib().p2b_partial_products_and_zs(ctx.handle, dw.ptr, ds.ptr, n.bit_length() - 1, nr, quotient_degree_factor, nc, arr(k_is),
+                                             arr(betas), arr(gammas), out.ptr))
+    return out, (nc * K, n)
 
 
 class Challenger:

@@ -61,7 +61,10 @@ __device__ __noinline__ void duplex(Challenger* c) {
   u64 s[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = c->state[i];
-  for (u32 i = 0; i < c->in_len && i < 8; i++) s[i] = c->in[i];
+  const u32 filled = c->in_len;
+#pragma unroll
+  for (int i = 0; i < 8; i++)  // static indices only: the state must stay in registers
+    if ((u32)i < filled) s[i] = c->in[i];
   c->in_len = 0;
   poseidon::permute(s);
 #pragma unroll
@@ -107,10 +110,11 @@ __global__ void __launch_bounds__(128) pow_search_kernel(const Challenger* __res
 #pragma unroll
   for (int k = 0; k < 12; k++) s[k] = c->state[k];
   const u32 pos = c->in_len;
-  for (u32 k = 0; k < pos && k < 8; k++) s[k] = c->in[k];
 #pragma unroll
-  for (int k = 0; k < 8; k++)
+  for (int k = 0; k < 8; k++) {  // static indices only: the state must stay in registers
+    if ((u32)k < pos) s[k] = c->in[k];
     if ((u32)k == pos) s[k] = cand;
+  }
   poseidon::permute(s);
   u64 resp = gl::canon(s[7]);
   u32 lz = resp ? (u32)__clzll((long long)resp) : 64u;

@@ -37,8 +37,13 @@ struct p2b_fri_proof {
   std::vector<std::vector<u64>> step_evals, step_sibs;
   u64 alpha[2] = {0, 0};
   std::vector<u64> betas;                      // [round][2]
-  std::vector<u64> final_in;                   // [n][2]
+  // the polynomial that enters FRI stays on the device ([2][n] columns); copied out only when a test asks for it
+  p2b_ctx* ctx = nullptr;
+  u64* d_final_in = nullptr;
+  u64 final_in_len = 0;
 };
+
+extern "C" void p2b_fri_proof_destroy(p2b_fri_proof* p);
 
 // coset LDE of an extension polynomial: coeffs [2][2^k] -> rows [2^(k+rate_bits)][2] (bit-reversed order), on shift * H
 static int fri_ext_lde(p2b_ctx* c, const u64* coeffs, u32 k, u32 rate_bits, u64 shift, u64* rows) {
@@ -159,7 +164,10 @@ extern "C" int p2b_fri_prove_openings(p2b_ctx* c, const p2b_batch* const* oracle
 
     // ---- final polynomial (oracle.rs:1060-1084) ----
     P2B_TRY(dalloc((void**)&comp, 2 * n * sizeof(u64)));
-    P2B_TRY(dalloc((void**)&fin, 2 * n * sizeof(u64)));
+    CUDA_TRY(cudaMallocAsync(&fin, 2 * n * sizeof(u64), st));
+    pr->ctx = c;
+    pr->d_final_in = fin;
+    pr->final_in_len = n;
     // exponent list: per batch the alpha-power table 0..count-1, then one weight per batch
     std::vector<u64> exps;
     std::vector<u64> table_off(num_batches), weight_exp(num_batches, 0);
@@ -210,9 +218,6 @@ extern "C" int p2b_fri_prove_openings(p2b_ctx* c, const p2b_batch* const* oracle
       c->launches += 4;
       CUDA_TRY(cudaGetLastError());
     }
-    pr->final_in.resize(2 * n);
-    std::vector<u64> fin_cols(2 * n);
-    CUDA_TRY(cudaMemcpyAsync(fin_cols.data(), fin, 2 * n * sizeof(u64), cudaMemcpyDeviceToHost, st));
 
     // ---- commit phase (oracle.rs:1086-1092, prover.rs:76-120) ----
     // coefficients are kept as their non-zero prefix [2][n_i]; the LDE zero-pads by 2^rate_bits like lde() + coset_fft
@@ -262,7 +267,9 @@ extern "C" int p2b_fri_prove_openings(p2b_ctx* c, const p2b_batch* const* oracle
     unsigned long long* d_found = (unsigned long long*)(d_small + off_found);
     CUDA_TRY(cudaMemsetAsync(d_found, 0xff, sizeof(u64), st));
     u64 found = ~(u64)0;
-    const u64 batch = (u64)1 << 22;
+    // candidates are searched in increasing order, one launch per contiguous range sized ~4x the expected number of
+    // tries (2^proof_of_work_bits), so the first launch succeeds with probability ~98% and little work is wasted
+    const u64 batch = (u64)1 << std::min<u32>(24, std::max<u32>(14, min_lz + 2));
     for (u64 base = 0; found == ~(u64)0; base += batch) {
       if (base >= gl::P - batch) return fail(P2B_ERR_INVALID, "Proof of work failed. This is highly unlikely!");
       fri::pow_search_kernel<<<(unsigned)(batch / 128), 128, 0, st>>>(d_ch, base, batch, min_lz, d_found);
@@ -286,10 +293,6 @@ extern "C" int p2b_fri_prove_openings(p2b_ctx* c, const p2b_batch* const* oracle
     pr->indices.assign(small.begin() + off_idx, small.end());
     u32 resp_lz = pr->pow_response ? (u32)__builtin_clzll(pr->pow_response) : 64u;
     if (resp_lz < min_lz) return fail(P2B_ERR_INVALID, "internal: proof-of-work response does not verify");
-    for (u64 i = 0; i < n; i++) {
-      pr->final_in[2 * i] = fin_cols[i];
-      pr->final_in[2 * i + 1] = fin_cols[n + i];
-    }
     pr->final_poly.resize(2 * flen);
     for (u64 i = 0; i < flen; i++) {
       pr->final_poly[2 * i] = fcols[i];
@@ -332,14 +335,18 @@ extern "C" int p2b_fri_prove_openings(p2b_ctx* c, const p2b_batch* const* oracle
   for (p2b_batch* t : trees) batch_free(t);
   if (rc != P2B_OK) {
     cudaStreamSynchronize(st);
-    delete pr;
+    p2b_fri_proof_destroy(pr);
     return rc;
   }
   *out = pr;
   return P2B_OK;
 }
 
-extern "C" void p2b_fri_proof_destroy(p2b_fri_proof* p) { delete p; }
+extern "C" void p2b_fri_proof_destroy(p2b_fri_proof* p) {
+  if (!p) return;
+  if (p->d_final_in) cudaFreeAsync(p->d_final_in, p->ctx->stream);
+  delete p;
+}
 extern "C" int p2b_fri_proof_get_info(const p2b_fri_proof* p, p2b_fri_proof_info* out) {
   if (!p || !out) return fail(P2B_ERR_INVALID, "NULL argument");
   *out = p->info;
@@ -389,7 +396,17 @@ extern "C" int p2b_fri_proof_get_debug(const p2b_fri_proof* p, uint32_t what, ui
   switch (what) {
     case 0: out[0] = p->alpha[0]; out[1] = p->alpha[1]; return P2B_OK;
     case 1: return p->betas.empty() ? P2B_OK : copy_out(p->betas, out);
-    case 2: return copy_out(p->final_in, out);
+    case 2: {
+      const u64 n = p->final_in_len;
+      std::vector<u64> cols(2 * n);
+      CUDA_TRY(cudaMemcpyAsync(cols.data(), p->d_final_in, 2 * n * sizeof(u64), cudaMemcpyDeviceToHost, p->ctx->stream));
+      CUDA_TRY(cudaStreamSynchronize(p->ctx->stream));
+      for (u64 i = 0; i < n; i++) {
+        out[2 * i] = cols[i];
+        out[2 * i + 1] = cols[n + i];
+      }
+      return P2B_OK;
+    }
     case 3: out[0] = p->pow_response; return P2B_OK;
     default: return fail(P2B_ERR_INVALID, "unknown debug selector %u", what);
   }

@@ -31,6 +31,7 @@
 #include "ntt.cuh"
 #include "quotient.cuh"
 #include "fri.cuh"
+#include "permutation.cuh"
 
 using gl::u32;
 using gl::u64;
@@ -1169,6 +1170,57 @@ extern "C" int p2b_quotient_polys(p2b_ctx* ctx, const p2b_circuit* circuit, cons
   if (zs_pp->info.num_polys < (u64)circuit->num_challenges * (1 + npp)) return fail(P2B_ERR_INVALID, "zs/partial-products batch has too few columns");
   return quotient_impl(ctx, circuit, wires->leaves, wires->info.leaf_len, zs_pp->leaves, zs_pp->info.leaf_len, consts_sigmas->leaves,
                        consts_sigmas->info.leaf_len, public_inputs_hash, betas, gammas, alphas, d_values_out, d_coeffs_out, nullptr);
+}
+
+
+// ======================================================================================================
+// permutation argument: Z and partial products (plonk/prover.rs:702-786, :112-117)
+// ======================================================================================================
+extern "C" int p2b_partial_products_and_zs(p2b_ctx* c, const uint64_t* d_wires_values, const uint64_t* d_sigma_values,
+                                           uint32_t degree_bits, uint32_t num_routed_wires, uint32_t quotient_degree_factor,
+                                           uint32_t num_challenges, const uint64_t* k_is, const uint64_t* betas,
+                                           const uint64_t* gammas, uint64_t* d_out) {
+  if (!c || !d_wires_values || !d_sigma_values || !k_is || !betas || !gammas || !d_out) return fail(P2B_ERR_INVALID, "NULL argument");
+  if (degree_bits > 32) return fail(P2B_ERR_INVALID, "degree_bits exceeds the field's two-adicity 32");
+  if (num_challenges == 0 || num_challenges > (u32)perm::MAX_CH) return fail(P2B_ERR_INVALID, "num_challenges must be in [1, %d]", perm::MAX_CH);
+  if (quotient_degree_factor < 2) return fail(P2B_ERR_INVALID, "quotient_degree_factor must be at least 2");
+  if (!(quotient_degree_factor < num_routed_wires))  // prover.rs:102-105
+    return fail(P2B_ERR_INVALID, "When the number of routed wires is smaller that the degree, we should change the logic to avoid computing partial products.");
+  const u32 K = (num_routed_wires + quotient_degree_factor - 1) / quotient_degree_factor;
+  if (K > 64) return fail(P2B_ERR_UNSUPPORTED, "more than 64 partial-product chunks (%u)", K);
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const u64 n = (u64)1 << degree_bits;
+  const u32 nb = (u32)((n + perm::SCAN_BLOCK - 1) / perm::SCAN_BLOCK);
+  perm::Challenges ch{};
+  for (u32 i = 0; i < num_challenges; i++) {
+    ch.beta[i] = betas[i] % gl::P;
+    ch.gamma[i] = gammas[i] % gl::P;
+  }
+  u64 *d_kis = nullptr, *d_tot = nullptr;
+  auto body = [&]() -> int {
+    CUDA_TRY(cudaMallocAsync(&d_kis, num_routed_wires * sizeof(u64), st));
+    CUDA_TRY(cudaMallocAsync(&d_tot, (u64)num_challenges * nb * sizeof(u64), st));
+    CUDA_TRY(cudaMemcpyAsync(d_kis, k_is, num_routed_wires * sizeof(u64), cudaMemcpyHostToDevice, st));
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    const u64 w = hostf::root(degree_bits);
+    if (K <= 16)
+      perm::chunk_products_kernel<16><<<blocks, 128, 0, st>>>(d_wires_values, d_sigma_values, n, degree_bits, num_routed_wires,
+                                                              quotient_degree_factor, num_challenges, ch, d_kis, w, d_out);
+    else
+      perm::chunk_products_kernel<64><<<blocks, 128, 0, st>>>(d_wires_values, d_sigma_values, n, degree_bits, num_routed_wires,
+                                                              quotient_degree_factor, num_challenges, ch, d_kis, w, d_out);
+    perm::block_totals_kernel<<<dim3(nb, num_challenges), perm::SCAN_BLOCK, 0, st>>>(d_out, n, nb, d_tot);
+    perm::scan_totals_kernel<<<num_challenges, perm::SCAN_BLOCK, 0, st>>>(d_tot, nb);
+    perm::apply_kernel<<<dim3(nb, num_challenges), perm::SCAN_BLOCK, 0, st>>>(d_out, n, nb, num_challenges, K, d_tot);
+    c->launches += 4;
+    CUDA_TRY(cudaGetLastError());
+    return P2B_OK;
+  };
+  int rc = body();
+  if (d_kis) cudaFreeAsync(d_kis, st);
+  if (d_tot) cudaFreeAsync(d_tot, st);
+  return rc;
 }
 
 #include "fri_api.cuh"
