@@ -12,8 +12,8 @@ from PolynomialBatch::from_values' own structure: `values.into_par_iter().map(if
 fill_digests_buf's independent cap sub-trees (hash/merkle_tree.rs:232-243).
 
 The orchestration is written against two small interfaces so that the host-side logic is testable on CPU with gloo:
-  engine : ifft_columns / commit_blocks / export_top / import_nodes / finish_layers / cap   (GpuEngine = the C ABI)
-  comm   : rank, world, all_gather(array-like) -> list                                      (TorchComm = torch.distributed)
+  engine : ifft_columns / commit_blocks / export_nodes / import_nodes / finish_layers / cap / pack_open_rows   (GpuEngine = the C ABI)
+  comm   : rank, world, all_gather_columns / all_gather_nodes / all_reduce_sum                                  (TorchComm = torch.distributed)
 """
 import ctypes as C
 import math
@@ -83,6 +83,23 @@ def sharded_commit_from_values(engine, comm, values_shard, num_polys, n_log, rat
     return batch
 
 
+def sharded_open_rows(engine, comm, batch, indices, n_log, rate_bits, cap_height, leaf_len):
+    """FRI query openings over a sharded batch (fri/prover.rs:187-216: `t.get(x_index)`, `t.prove(x_index)` for every
+    query): the rank that owns leaf x (contiguous range [rank*N/G, (rank+1)*N/G)) gathers the row and its Merkle path --
+    its own digests below the local top layer, the layers above are complete on every rank after
+    sharded_commit_from_values -- and one all-reduce (sum; every query has exactly one owner, the others contribute
+    zeros) hands all rows and paths to every rank.  Returns (rows [Q][leaf_len], siblings [Q][layers][4]) as uint64."""
+    rank, world = comm.rank, comm.world
+    per = (1 << (n_log + rate_bits)) // world
+    layers = n_log + rate_bits - cap_height
+    width = leaf_len + 4 * layers
+    mine = [k for k, x in enumerate(indices) if x // per == rank]
+    packed = engine.pack_open_rows(batch, [indices[k] for k in mine], mine, len(indices), leaf_len, layers)  # [Q][width]
+    total = comm.all_reduce_sum(packed)
+    a = engine.to_numpy(total).reshape(len(indices), width)
+    return a[:, :leaf_len].copy(), a[:, leaf_len:].reshape(len(indices), layers, 4).copy()
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # GPU engine / torch.distributed communicator
 # ---------------------------------------------------------------------------------------------------------------
@@ -128,6 +145,17 @@ class GpuEngine:
     def cap(self, batch):
         return batch.cap()
 
+    def pack_open_rows(self, batch, idx, slots, Q, leaf_len, layers):
+        packed = np.zeros((Q, leaf_len + 4 * layers), dtype=np.uint64)
+        if idx:
+            rows, sibs = batch.open_rows(idx)      # open_rows_kernel gathers rows + paths on the device
+            packed[slots, :leaf_len] = rows
+            packed[slots, leaf_len:] = sibs.reshape(len(idx), -1)
+        return self.torch.from_numpy(packed.view(np.int64)).cuda()
+
+    def to_numpy(self, t):
+        return t.cpu().numpy().view(np.uint64)
+
 
 class TorchComm:
     """torch.distributed (NCCL on GPUs, gloo on CPU) behind the two collectives the path needs."""
@@ -151,3 +179,8 @@ class TorchComm:
 
     def all_gather_nodes(self, t, count):
         return self._gather(t)
+
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return t

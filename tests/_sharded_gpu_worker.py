@@ -40,6 +40,12 @@ def main():
         rows, sibs = b.open_rows(idx)
         for r, s, i in zip(rows, sibs, idx):
             good = good and oracle.merkle_verify(r, i, b.cap(), s)
+        # FRI query openings across the shards (rows owned by different ranks, gathered with one all-reduce)
+        N = n << rate_bits
+        qidx = [0, N - 1, N // 2, N // 2 - 1, 1, N // 4 + 3]
+        qrows, qsibs = sharded.sharded_open_rows(engine, comm, b, qidx, n_log, rate_bits, cap_height, P)
+        for x, r, sb in zip(qidx, qrows, qsibs):
+            good = good and np.array_equal(r, ref.leaves[x]) and np.array_equal(sb, oracle.merkle_prove(ref.digests, N, cap_height, x))
         if not good:
             print("rank %d MISMATCH for" % rank, (n_log, P, rate_bits, cap_height), flush=True)
         ok = ok and good

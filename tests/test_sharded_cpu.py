@@ -83,7 +83,7 @@ class OracleEngine:
             l += 1
         digests = np.where(mask_d[:, None], full.digests, np.uint64(0xDEADBEEF))
         return {"leaves": full.leaves[leaf0:leaf1], "digests": digests, "cap": cap, "sub_log": sub_log, "sub_d": sub_d,
-                "N": N, "top": top, "coeffs": co.copy()}
+                "N": N, "top": top, "coeffs": co.copy(), "leaf0": leaf0}
 
     def export_nodes(self, b, layer, first, count):
         out = np.empty((count, 4), dtype=np.uint64)
@@ -113,6 +113,19 @@ class OracleEngine:
     def cap(self, b):
         return b["cap"]
 
+    def pack_open_rows(self, b, idx, slots, Q, leaf_len, layers):
+        packed = np.zeros((Q, leaf_len + 4 * layers), dtype=np.uint64)
+        for x, slot in zip(idx, slots):
+            packed[slot, :leaf_len] = b["leaves"][x - b["leaf0"]]
+            for l in range(layers):   # MerkleTree::prove (merkle_tree.rs:392-440): sibling of the layer-l ancestor
+                where, i = sharded.node_index(b["sub_log"], b["sub_d"], l, (x >> l) ^ 1)
+                assert where == "digests"
+                packed[slot, leaf_len + 4 * l: leaf_len + 4 * l + 4] = b["digests"][i]
+        return torch.from_numpy(packed.view(np.int64))
+
+    def to_numpy(self, t):
+        return t.numpy().view(np.uint64)
+
 
 def _free_port():
     s = socket.socket()
@@ -140,6 +153,13 @@ def _worker(rank, world, port, n_log, P, rate_bits, cap_height, q):
         n = 1 << n_log
         b0, bc = sharded.block_shard(rate_bits, world, rank)
         ok = ok and np.array_equal(batch["leaves"], ref.leaves[b0 * n:(b0 + bc) * n])
+        # FRI query openings: rows + Merkle paths of leaves owned by different ranks reach every rank
+        N = n << rate_bits
+        idx = [0, N - 1, N // 2, (N // 2 - 1) % N, 1 % N]
+        rows, sibs = sharded.sharded_open_rows(OracleEngine(), comm, batch, idx, n_log, rate_bits, cap_height, P)
+        for x, r, sb in zip(idx, rows, sibs):
+            ok = ok and np.array_equal(r, ref.leaves[x]) and oracle.merkle_verify(r, x, ref.cap, sb)
+            ok = ok and np.array_equal(sb, oracle.merkle_prove(ref.digests, N, cap_height, x))
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
