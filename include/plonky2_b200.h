@@ -157,7 +157,12 @@ int p2b_batch_finish_layers(p2b_batch* b, uint32_t from_layer);
  *                  NOOP -, CONSTANT p0=num_consts, PUBLIC_INPUT -, ARITHMETIC p0=num_ops, BASE_SUM p0=num_limbs p1=B,
  *                  POSEIDON -, RANDOM_ACCESS p0=bits p1=num_copies p2=num_extra_constants, U32_ARITHMETIC p0=num_ops,
  *                  U32_ADD_MANY p0=num_addends p1=num_ops, U32_RANGE_CHECK p0=num_input_limbs, U32_SUBTRACTION p0=num_ops,
- *                  COMPARISON p0=num_bits p1=num_chunks
+ *                  COMPARISON p0=num_bits p1=num_chunks, ARITHMETIC_EXTENSION / MUL_EXTENSION p0=num_ops,
+ *                  REDUCING / REDUCING_EXTENSION p0=num_coeffs, EXPONENTIATION p0=num_power_bits, POSEIDON_MDS -,
+ *                  HIGH_ / LOW_DEGREE_INTERPOLATION p0=subgroup_bits (1..8)
+ *                  (gates/arithmetic_extension.rs:129, multiplication_extension.rs:122, reducing.rs:160,
+ *                  reducing_extension.rs:160, exponentiation.rs:266, poseidon_mds.rs:184, high_degree_interpolation.rs:126,
+ *                  low_degree_interpolation.rs:356)
  *   rows       : the three commitments' leaf rows as the commit produces them (row L = LDE point reverse_bits(L)):
  *                wires [num_wires..], zs_partial_products [num_challenges * (1 + num_partial_products)..],
  *                constants_sigmas [num_constants + num_routed_wires..]; trailing salt columns are ignored.
@@ -167,7 +172,11 @@ int p2b_batch_finish_layers(p2b_batch* b, uint32_t from_layer);
 enum {
   P2B_GATE_NOOP = 0, P2B_GATE_CONSTANT = 1, P2B_GATE_PUBLIC_INPUT = 2, P2B_GATE_ARITHMETIC = 3, P2B_GATE_BASE_SUM = 4,
   P2B_GATE_POSEIDON = 5, P2B_GATE_RANDOM_ACCESS = 6, P2B_GATE_U32_ARITHMETIC = 7, P2B_GATE_U32_ADD_MANY = 8,
-  P2B_GATE_U32_RANGE_CHECK = 9, P2B_GATE_U32_SUBTRACTION = 10, P2B_GATE_COMPARISON = 11
+  P2B_GATE_U32_RANGE_CHECK = 9, P2B_GATE_U32_SUBTRACTION = 10, P2B_GATE_COMPARISON = 11,
+  /* recursion gate set; an extension element = 2 consecutive wires */
+  P2B_GATE_ARITHMETIC_EXTENSION = 12, P2B_GATE_MUL_EXTENSION = 13, P2B_GATE_REDUCING = 14, P2B_GATE_REDUCING_EXTENSION = 15,
+  P2B_GATE_EXPONENTIATION = 16, P2B_GATE_POSEIDON_MDS = 17, P2B_GATE_HIGH_DEGREE_INTERPOLATION = 18,
+  P2B_GATE_LOW_DEGREE_INTERPOLATION = 19
 };
 typedef struct {
   uint32_t type, selector_index, group_start, group_end; /* group = gate index range [start, end) of its selector */

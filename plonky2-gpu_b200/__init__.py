@@ -93,6 +93,8 @@ class FriProofInfo(C.Structure):
 
 GATE_NOOP, GATE_CONSTANT, GATE_PUBLIC_INPUT, GATE_ARITHMETIC, GATE_BASE_SUM, GATE_POSEIDON, GATE_RANDOM_ACCESS = range(7)
 GATE_U32_ARITHMETIC, GATE_U32_ADD_MANY, GATE_U32_RANGE_CHECK, GATE_U32_SUBTRACTION, GATE_COMPARISON = range(7, 12)
+(GATE_ARITHMETIC_EXTENSION, GATE_MUL_EXTENSION, GATE_REDUCING, GATE_REDUCING_EXTENSION, GATE_EXPONENTIATION, GATE_POSEIDON_MDS,
+ GATE_HIGH_DEGREE_INTERPOLATION, GATE_LOW_DEGREE_INTERPOLATION) = range(12, 20)
 
 
 class Circuit:

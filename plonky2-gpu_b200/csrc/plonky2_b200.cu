@@ -1062,6 +1062,10 @@ static int quotient_impl(p2b_ctx* c, const p2b_circuit* circ, const u64* d_wires
       return fail(P2B_ERR_INVALID, "gate %u: bad selector group", i);
     if (g.type == quotient::G_RANDOM_ACCESS && g.p0 > 6) return fail(P2B_ERR_UNSUPPORTED, "RandomAccessGate with more than 6 bits");
     if (g.type == quotient::G_COMPARISON && g.p1 == 0) return fail(P2B_ERR_INVALID, "ComparisonGate with zero chunks");
+    if ((g.type == quotient::G_HIGH_DEGREE_INTERPOLATION || g.type == quotient::G_LOW_DEGREE_INTERPOLATION) && (g.p0 == 0 || g.p0 > 8))
+      return fail(P2B_ERR_UNSUPPORTED, "interpolation gate with subgroup_bits %u outside [1, 8]", g.p0);
+    if ((g.type == quotient::G_REDUCING || g.type == quotient::G_REDUCING_EXT || g.type == quotient::G_EXPONENTIATION) && g.p0 == 0)
+      return fail(P2B_ERR_INVALID, "gate %u: zero coefficients / power bits", i);
     gates[i] = quotient::GateDesc{g.type, g.selector_index, g.group_start, g.group_end, g.p0, g.p1, g.p2, 0};
     u32 k = quotient::gate_num_constraints(gates[i]);
     ngc = k > ngc ? k : ngc;
@@ -1086,6 +1090,7 @@ static int quotient_impl(p2b_ctx* c, const p2b_circuit* circ, const u64* d_wires
   }
   p.w = hostf::root(circ->degree_bits + qdb);
   p.n_field = ((u64)1 << circ->degree_bits) % gl::P;
+  for (u32 i = 0; i <= 8; i++) p.small_roots[i] = hostf::root(i);
   p.wires = d_wires;
   p.wires_stride = wires_stride;
   p.zs_pp = d_zs_pp;

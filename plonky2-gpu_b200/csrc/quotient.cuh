@@ -26,7 +26,10 @@ using gl::u64;
 
 enum GateType : u32 {
   G_NOOP = 0, G_CONSTANT = 1, G_PUBLIC_INPUT = 2, G_ARITHMETIC = 3, G_BASE_SUM = 4, G_POSEIDON = 5, G_RANDOM_ACCESS = 6,
-  G_U32_ARITHMETIC = 7, G_U32_ADD_MANY = 8, G_U32_RANGE_CHECK = 9, G_U32_SUBTRACTION = 10, G_COMPARISON = 11, G_NUM_TYPES = 12
+  G_U32_ARITHMETIC = 7, G_U32_ADD_MANY = 8, G_U32_RANGE_CHECK = 9, G_U32_SUBTRACTION = 10, G_COMPARISON = 11,
+  // the gates a recursive-verifier circuit adds (extension elements = 2 consecutive wires)
+  G_ARITHMETIC_EXT = 12, G_MUL_EXT = 13, G_REDUCING = 14, G_REDUCING_EXT = 15, G_EXPONENTIATION = 16, G_POSEIDON_MDS = 17,
+  G_HIGH_DEGREE_INTERPOLATION = 18, G_LOW_DEGREE_INTERPOLATION = 19, G_NUM_TYPES = 20
 };
 
 struct GateDesc {  // == p2b_gate
@@ -51,6 +54,7 @@ struct Params {
   u64 zh[MAX_ZH], zh_inv[MAX_ZH];       // Z_H on the coset and inverses, indexed i mod 2^qdb
   u64 w;                                // generator of the evaluation subgroup (order 2^(degree_bits + qdb))
   u64 n_field;                          // n as a field element
+  u64 small_roots[9];                   // primitive_root_of_unity(k), k <= 8 (interpolation gates' cosets)
   u64* out_values;                      // [num_challenges][lde_size]
   u64* out_rows;                        // optional [lde_size][num_challenges] (the reference's d_outs layout)
 };
@@ -70,6 +74,14 @@ __host__ __device__ inline u32 gate_num_constraints(const GateDesc& g) {
     case G_U32_RANGE_CHECK: return g.p0 * 17;
     case G_U32_SUBTRACTION: return g.p0 * 19;
     case G_COMPARISON: return 6 + 5 * g.p1 + (g.p0 + g.p1 - 1) / g.p1;
+    case G_ARITHMETIC_EXT: return 2 * g.p0;
+    case G_MUL_EXT: return 2 * g.p0;
+    case G_REDUCING: return 2 * g.p0;
+    case G_REDUCING_EXT: return 2 * g.p0;
+    case G_EXPONENTIATION: return g.p0 + 1;
+    case G_POSEIDON_MDS: return 24;
+    case G_HIGH_DEGREE_INTERPOLATION: return 2 * (1u << g.p0) + 2;
+    case G_LOW_DEGREE_INTERPOLATION: return ((1u << g.p0) - 2) + 2 * (1u << g.p0) + 2 * ((1u << g.p0) - 2) + 2;
     default: return 0;
   }
 }
@@ -266,6 +278,124 @@ __device__ __forceinline__ void eval_comparison(const GateDesc& g, const u64* w,
   e.emit(fsub(fadd(W(3), 1ull << cb), bits_comb));
   e.emit(fsub(W(2), W(4 + 5 * nc + cb)));
 }
+// ---- recursion gate set: quadratic-extension arithmetic on wire pairs (field/src/extension/quadratic.rs:172-185) ----
+struct X2 {
+  u64 a, b;
+};
+#define WX(k) X2{W(k), W((k) + 1)}
+__device__ __forceinline__ X2 xadd(X2 x, X2 y) { return X2{fadd(x.a, y.a), fadd(x.b, y.b)}; }
+__device__ __forceinline__ X2 xsub(X2 x, X2 y) { return X2{fsub(x.a, y.a), fsub(x.b, y.b)}; }
+template <class M>
+__device__ __forceinline__ X2 xmul(X2 x, X2 y, Emitter<M>& e) {
+  u64 t = e.mul(x.b, y.b);
+  return X2{e.mul_add(x.a, y.a, e.mul(7, t)), e.mul_add(x.a, y.b, e.mul(x.b, y.a))};
+}
+template <class M>
+__device__ __forceinline__ X2 xscale(X2 x, u64 s, Emitter<M>& e) { return X2{e.mul(x.a, s), e.mul(x.b, s)}; }
+template <class M>
+__device__ __forceinline__ void emit2(X2 v, Emitter<M>& e) {  // yield_constr.many(x.to_basefield_array())
+  e.emit(v.a);
+  e.emit(v.b);
+}
+template <class M>
+__device__ __forceinline__ void eval_arithmetic_ext(const GateDesc& g, const u64* w, const u64* kc, Emitter<M>& e) {  // arithmetic_extension.rs:129-147
+  const u64 c0 = K(0), c1 = K(1);
+  for (u32 i = 0; i < g.p0; i++) {
+    X2 computed = xadd(xscale(xmul(WX(8 * i), WX(8 * i + 2), e), c0, e), xscale(WX(8 * i + 4), c1, e));
+    emit2(xsub(WX(8 * i + 6), computed), e);
+  }
+}
+template <class M>
+__device__ __forceinline__ void eval_mul_ext(const GateDesc& g, const u64* w, const u64* kc, Emitter<M>& e) {  // multiplication_extension.rs:122-137
+  const u64 c0 = K(0);
+  for (u32 i = 0; i < g.p0; i++) emit2(xsub(WX(6 * i + 4), xscale(xmul(WX(6 * i), WX(6 * i + 2), e), c0, e)), e);
+}
+// reducing.rs:160-180 (EXT = false: base-field coefficients, one wire each) / reducing_extension.rs:160-179 (EXT = true)
+template <bool EXT, class M>
+__device__ __forceinline__ void eval_reducing(const GateDesc& g, const u64* w, Emitter<M>& e) {
+  const u32 n = g.p0, cw = EXT ? 2 : 1, start_accs = 6 + cw * n;
+  const X2 alpha = WX(2);
+  X2 acc = WX(4);
+  for (u32 i = 0; i < n; i++) {
+    const X2 coeff = EXT ? WX(6 + 2 * i) : X2{W(6 + i), 0};
+    const X2 a = i + 1 == n ? WX(0) : WX(start_accs + 2 * i);  // the last accumulator is the output
+    emit2(xsub(xadd(xmul(acc, alpha, e), coeff), a), e);
+    acc = a;
+  }
+}
+template <class M>
+__device__ __forceinline__ void eval_exponentiation(const GateDesc& g, const u64* w, Emitter<M>& e) {  // exponentiation.rs:266-299
+  const u32 nb = g.p0;
+  const u64 base = W(0);
+  u64 prev_inter = 0;
+  for (u32 i = 0; i < nb; i++) {
+    const u64 prev = i == 0 ? 1 : e.mul(prev_inter, prev_inter);
+    const u64 bit = W(1 + (nb - 1 - i));  // little-endian bits, accumulated from the top
+    const u64 inter = W(2 + nb + i);
+    e.emit(fsub(e.mul(prev, fadd(e.mul(bit, base), fsub(1, bit))), inter));
+    prev_inter = inter;
+  }
+  e.emit(fsub(W(1 + nb), prev_inter));
+}
+template <class M>
+__device__ __forceinline__ void eval_poseidon_mds(const u64* w, Emitter<M>& e) {  // poseidon_mds.rs:184-203
+  for (u32 r = 0; r < 12; r++) {
+    X2 acc{0, 0};
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      const u32 k = 2 * ((i + r) % 12);
+      acc.a = e.mul_add(W(k), (u64)poseidon::mds_circ(i), acc.a);
+      acc.b = e.mul_add(W(k + 1), (u64)poseidon::mds_circ(i), acc.b);
+    }
+    if (r == 0) {  // MDS_MATRIX_DIAG = [8, 0, ...]
+      acc.a = e.mul_add(W(0), (u64)poseidon::MDS_DIAG0, acc.a);
+      acc.b = e.mul_add(W(1), (u64)poseidon::MDS_DIAG0, acc.b);
+    }
+    emit2(xsub(WX(24 + 2 * r), acc), e);
+  }
+}
+// gates/interpolation.rs:21-76 layout: shift 0 | values 1.. | evaluation point | evaluation value | coefficients
+template <class M>
+__device__ __forceinline__ void eval_high_degree_interpolation(const GateDesc& g, const u64* w, const u64* roots, Emitter<M>& e) {  // high_degree_interpolation.rs:126-147
+  const u32 np = 1u << g.p0, ep_w = 1 + 2 * np, ev_w = ep_w + 2, coeffs_w = ev_w + 2;
+  const u64 gen = roots[g.p0];
+  u64 point = W(0);
+  for (u32 i = 0; i < np; i++) {
+    X2 acc{0, 0};
+    for (u32 k = np; k-- > 0;) acc = xadd(xscale(acc, point, e), WX(coeffs_w + 2 * k));  // eval_base
+    emit2(xsub(WX(1 + 2 * i), acc), e);
+    point = e.mul(point, gen);
+  }
+  const X2 ep = WX(ep_w);
+  X2 acc{0, 0};
+  for (u32 k = np; k-- > 0;) acc = xadd(xmul(acc, ep, e), WX(coeffs_w + 2 * k));
+  emit2(xsub(WX(ev_w), acc), e);
+}
+template <class M>
+__device__ __forceinline__ void eval_low_degree_interpolation(const GateDesc& g, const u64* w, const u64* roots, Emitter<M>& e) {  // low_degree_interpolation.rs:356-404
+  const u32 np = 1u << g.p0, ep_w = 1 + 2 * np, ev_w = ep_w + 2, coeffs_w = ev_w + 2, end_coeffs = coeffs_w + 2 * np;
+  auto shift_pow_w = [&](u32 i) { return i == 1 ? 0u : end_coeffs + i - 2; };                     // :50-57
+  auto eval_pow_w = [&](u32 i) { return i == 1 ? ep_w : end_coeffs + np - 2 + 2 * (i - 2); };     // :59-67
+  const u64 shift = W(0);
+  for (u32 i = 1; i + 1 < np; i++) e.emit(fsub(e.mul(W(shift_pow_w(i)), shift), W(shift_pow_w(i + 1))));
+  const u64 gen = roots[g.p0];
+  u64 point = 1;
+  for (u32 i = 0; i < np; i++) {
+    X2 acc{0, 0};
+    for (u32 k = np; k-- > 0;) {  // altered coefficient k = c_k * shift^k
+      X2 c = WX(coeffs_w + 2 * k);
+      if (k) c = xscale(c, W(shift_pow_w(k)), e);
+      acc = xadd(xscale(acc, point, e), c);
+    }
+    emit2(xsub(WX(1 + 2 * i), acc), e);
+    point = e.mul(point, gen);
+  }
+  const X2 ep = WX(ep_w);
+  for (u32 i = 1; i + 1 < np; i++) emit2(xsub(xmul(WX(eval_pow_w(i)), ep, e), WX(eval_pow_w(i + 1))), e);
+  X2 acc = WX(coeffs_w);  // eval_with_powers
+  for (u32 k = 1; k < np; k++) acc = xadd(acc, xmul(WX(eval_pow_w(k)), WX(coeffs_w + 2 * k), e));
+  emit2(xsub(WX(ev_w), acc), e);
+}
 // gates/poseidon.rs:485-564
 template <class M>
 __device__ __forceinline__ void eval_poseidon(const u64* w, Emitter<M>& e) {
@@ -431,6 +561,14 @@ __device__ __forceinline__ void eval_point(const Params& p, const u64 i, const u
       case G_U32_RANGE_CHECK: eval_u32_range_check(g, w, e); break;
       case G_U32_SUBTRACTION: eval_u32_subtraction(g, w, e); break;
       case G_COMPARISON: eval_comparison(g, w, e); break;
+      case G_ARITHMETIC_EXT: eval_arithmetic_ext(g, w, kc, e); break;
+      case G_MUL_EXT: eval_mul_ext(g, w, kc, e); break;
+      case G_REDUCING: eval_reducing<false>(g, w, e); break;
+      case G_REDUCING_EXT: eval_reducing<true>(g, w, e); break;
+      case G_EXPONENTIATION: eval_exponentiation(g, w, e); break;
+      case G_POSEIDON_MDS: eval_poseidon_mds(w, e); break;
+      case G_HIGH_DEGREE_INTERPOLATION: eval_high_degree_interpolation(g, w, p.small_roots, e); break;
+      case G_LOW_DEGREE_INTERPOLATION: eval_low_degree_interpolation(g, w, p.small_roots, e); break;
       default: break;
     }
 #pragma unroll

@@ -8,6 +8,7 @@ import numpy as np
 
 import oracle
 from oracle import quotient as Q
+from oracle import recursion_gates as RG
 
 P = Q.P
 
@@ -107,12 +108,22 @@ def honest_row(gate, rng, num_wires, consts, pih):
         bits = [(val >> i) & 1 for i in range(cb + 1)]
         w[4 + 5 * nc:4 + 5 * nc + cb + 1] = bits
         w[2] = bits[cb]
+    elif isinstance(gate, RECURSION_GATES):
+        w = gate.honest_row(lambda: rnd(rng), num_wires, consts)
     else:
         raise TypeError(gate)
     return w
 
 
+RECURSION_GATES = (RG.ArithmeticExtensionGate, RG.MulExtensionGate, RG.ReducingGate, RG.ExponentiationGate, RG.PoseidonMdsGate,
+                   RG.HighDegreeInterpolationGate, RG.LowDegreeInterpolationGate)
+
+
 def gate_constants_needed(gate):
+    if isinstance(gate, RG.ArithmeticExtensionGate):
+        return 2
+    if isinstance(gate, RG.MulExtensionGate):
+        return 1
     if isinstance(gate, Q.ConstantGate):
         return gate.num_consts
     if isinstance(gate, Q.ArithmeticGate):
@@ -182,3 +193,17 @@ def standard_gate_sets(num_wires=135, num_routed=80):
     groups_b = groups_a + [(11, 12)]
     sel_b = sel_a + [3]
     return (mix, groups_a, sel_a), (with_pos, groups_b, sel_b)
+
+
+def recursion_gate_set(num_wires=135, num_routed=80):
+    """The gate types of a recursive-verifier circuit under standard_recursion_config (circuit_builder.rs + the gates
+    fri/recursive_verifier.rs and the hashing gadgets add), in groups that keep filter + gate degree within 8."""
+    gates = [Q.NoopGate(), Q.ConstantGate(2), Q.PublicInputGate(), Q.ArithmeticGate(num_routed // 4),
+             RG.ArithmeticExtensionGate(num_routed // 8), RG.MulExtensionGate(num_routed // 6),
+             RG.ReducingGate(min(num_routed - 6, (num_wires - 4) // 3)), RG.ReducingExtensionGate(min((num_routed - 6) // 2, (num_wires - 4) // 4)),
+             Q.BaseSumGate(min(63, num_routed - 1), 2), Q.RandomAccessGate.new_from_config(num_wires, num_routed, 4, 2),
+             RG.ExponentiationGate(min(num_routed - 2, (num_wires - 2) // 2)), RG.PoseidonMdsGate(),
+             RG.LowDegreeInterpolationGate(4), RG.HighDegreeInterpolationGate(2), Q.PoseidonGate()]
+    groups = [(0, 5), (5, 9), (9, 12), (12, 14), (14, 15)]
+    sel = [0] * 5 + [1] * 4 + [2] * 3 + [3] * 2 + [4]
+    return gates, groups, sel

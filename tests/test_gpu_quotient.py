@@ -53,6 +53,26 @@ def test_quotient_honest_witness_matches_oracle(ctx, which, degree_bits):
         assert not np.any(coeffs[c][7 * n:])  # honest witness: degree < 7n (size-independent property)
 
 
+@pytest.mark.parametrize("degree_bits,random_data", [(4, False), (5, True)])
+def test_quotient_recursion_gate_set_matches_oracle(ctx, degree_bits, random_data):
+    # the gates a recursive-verifier circuit adds: extension arithmetic, reducing, exponentiation, Poseidon MDS and both
+    # interpolation gates, on honest rows and on random data (every constraint non-zero)
+    gates, groups, sel = F.recursion_gate_set()
+    inst = F.build_instance(gates, groups, sel, degree_bits, 135, 80, seed=81)
+    if random_data:
+        rng = np.random.default_rng(82)
+        for m in (inst.wires, inst.zs_pp):
+            m[:] = rng.integers(0, P, size=m.shape, dtype=np.uint64)
+        inst.consts_sigmas[inst.circ.num_selectors:] = rng.integers(0, P, size=inst.consts_sigmas[inst.circ.num_selectors:].shape, dtype=np.uint64)
+    vals, coeffs, evals, ecoeffs = run_both(ctx, inst)
+    n = 1 << degree_bits
+    for c in range(inst.circ.num_challenges):
+        assert np.array_equal(vals[c], evals[c])
+        assert np.array_equal(coeffs[c], ecoeffs[c])
+        if not random_data:
+            assert not np.any(coeffs[c][7 * n:])  # honest rows: the numerator vanishes on H
+
+
 def test_quotient_random_data_matches_oracle(ctx):
     # no constraint holds on random data: every term of the alpha reduction is exercised with non-zero values,
     # including real partial products / Z columns and a non-identity sigma
