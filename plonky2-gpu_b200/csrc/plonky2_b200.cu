@@ -1125,7 +1125,21 @@ static int quotient_impl(p2b_ctx* c, const p2b_circuit* circ, const u64* d_wires
     p.alpha_pows = d_apows;
     p.out_values = vals;
     p.out_rows = d_rows_out;
-    quotient::quotient_values_kernel<<<(unsigned)((lde_size + 127) / 128), 128, 0, st>>>(p);
+    {
+#ifndef P2B_QUOT_PPT
+#define P2B_QUOT_PPT 1
+#endif
+      constexpr int PPT = P2B_QUOT_PPT;  // points per thread (quotient.cuh: eval_batch)
+      constexpr unsigned BD = P2B_QUOT_BLOCK;
+      const unsigned blocks = (unsigned)((lde_size + BD * PPT - 1) / (BD * PPT));
+      const size_t smem = (size_t)nc * PPT * BD * sizeof(u64);
+      switch (nc) {
+        case 1: quotient::quotient_values_kernel<1, PPT><<<blocks, BD, smem, st>>>(p); break;
+        case 2: quotient::quotient_values_kernel<2, PPT><<<blocks, BD, smem, st>>>(p); break;
+        case 3: quotient::quotient_values_kernel<3, PPT><<<blocks, BD, smem, st>>>(p); break;
+        default: quotient::quotient_values_kernel<4, PPT><<<blocks, BD, smem, st>>>(p); break;
+      }
+    }
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     if (d_coeffs_out) {

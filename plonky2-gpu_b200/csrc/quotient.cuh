@@ -88,7 +88,7 @@ __host__ __device__ inline u32 gate_num_constraints(const GateDesc& g) {
 
 // Accumulates sum_j alpha_c^(base + j) * c_j for every challenge; emit() is called in constraint order.  M = exact or
 // optimistic field reduction (gl64.cuh): the kernel evaluates a point optimistically and redoes it exactly if `rare`.
-template <class M>
+template <class M, int NC>
 struct Emitter {
   M& mode;
   __device__ __forceinline__ explicit Emitter(M& m) : mode(m) {}
@@ -100,23 +100,30 @@ struct Emitter {
     for (u32 x = 1; x < m; x++) p = mul(p, gl::sub_canonical(limb, x));
     return p;
   }
-  u64 acc[MAX_CHALLENGES];
+  // sum_j v_j * alpha_c^(base + j) accumulated UNREDUCED in 160 bits per challenge (v_j < 2^64, powers canonical: a gate
+  // has far fewer than 2^32 constraints) and reduced once per gate: a constraint costs a 64x64 multiply and a 3-word
+  // add per challenge instead of a full modular multiply-add
+  u64 lo[NC], hi[NC];
+  u32 top[NC];
   const u64* ap;  // alpha_pows + base
-  u32 stride, nc, j;
-  __device__ __forceinline__ void init(const u64* alpha_pows, u32 num_terms, u32 base, u32 nc_) {
+  u32 stride, j;
+  __device__ __forceinline__ void init(const u64* alpha_pows, u32 num_terms, u32 base) {
     ap = alpha_pows + base;
     stride = num_terms;
-    nc = nc_;
     j = 0;
 #pragma unroll
-    for (int c = 0; c < MAX_CHALLENGES; c++) acc[c] = 0;
+    for (int c = 0; c < NC; c++) {
+      lo[c] = 0;
+      hi[c] = 0;
+      top[c] = 0;
+    }
   }
   __device__ __forceinline__ void emit(u64 v) {
 #pragma unroll
-    for (int c = 0; c < MAX_CHALLENGES; c++)
-      if ((u32)c < nc) acc[c] = mul_add(v, __ldg(ap + (u64)c * stride + j), acc[c]);
+    for (int c = 0; c < NC; c++) poseidon::mac160(lo[c], hi[c], top[c], v, __ldg(ap + (u64)c * stride + j));
     j++;
   }
+  __device__ __forceinline__ u64 result(int c) { return poseidon::reduce160(lo[c], hi[c], top[c], mode); }
 };
 
 __device__ __forceinline__ u64 fsub(u64 a, u64 b) { return gl::sub(a, b); }
@@ -126,32 +133,32 @@ __device__ __forceinline__ u64 fadd(u64 a, u64 b) { return gl::add(a, b); }
 #define W(k) __ldg(w + (k))
 #define K(k) __ldg(kc + (k))
 
-template <class M>
-__device__ __forceinline__ void eval_constant(const GateDesc& g, const u64* w, const u64* kc, Emitter<M>& e) {  // constant.rs:150-158
+template <class E>
+__device__ __forceinline__ void eval_constant(const GateDesc& g, const u64* w, const u64* kc, E& e) {  // constant.rs:150-158
   for (u32 i = 0; i < g.p0; i++) e.emit(fsub(K(i), W(i)));
 }
-template <class M>
-__device__ __forceinline__ void eval_public_input(const u64* w, const u64* pih, Emitter<M>& e) {  // public_input.rs:129-139
+template <class E>
+__device__ __forceinline__ void eval_public_input(const u64* w, const u64* pih, E& e) {  // public_input.rs:129-139
   for (u32 i = 0; i < 4; i++) e.emit(fsub(W(i), pih[i]));
 }
-template <class M>
-__device__ __forceinline__ void eval_arithmetic(const GateDesc& g, const u64* w, const u64* kc, Emitter<M>& e) {  // arithmetic_base.rs:199-220
+template <class E>
+__device__ __forceinline__ void eval_arithmetic(const GateDesc& g, const u64* w, const u64* kc, E& e) {  // arithmetic_base.rs:199-220
   u64 c0 = K(0), c1 = K(1);
   for (u32 i = 0; i < g.p0; i++) {
     u64 computed = fadd(e.mul(e.mul(W(4 * i), W(4 * i + 1)), c0), e.mul(W(4 * i + 2), c1));
     e.emit(fsub(W(4 * i + 3), computed));
   }
 }
-template <class M>
-__device__ __forceinline__ void eval_base_sum(const GateDesc& g, const u64* w, Emitter<M>& e) {  // base_sum.rs:213-230
+template <class E>
+__device__ __forceinline__ void eval_base_sum(const GateDesc& g, const u64* w, E& e) {  // base_sum.rs:213-230
   const u32 nl = g.p0, B = g.p1;
   u64 sum = 0;
   for (u32 i = nl; i-- > 0;) sum = fadd(e.mul(sum, B), W(1 + i));
   e.emit(fsub(sum, W(0)));
   for (u32 i = 0; i < nl; i++) e.emit(e.range_product(W(1 + i), B));
 }
-template <class M>
-__device__ __forceinline__ void eval_random_access(const GateDesc& g, const u64* w, const u64* kc, Emitter<M>& e) {  // random_access.rs:409-450
+template <class E>
+__device__ __forceinline__ void eval_random_access(const GateDesc& g, const u64* w, const u64* kc, E& e) {  // random_access.rs:409-450
   const u32 bits = g.p0, copies = g.p1, extra = g.p2, vs = 1u << g.p0;
   const u32 routed = (2 + vs) * copies + extra;
   for (u32 copy = 0; copy < copies; copy++) {
@@ -177,8 +184,8 @@ __device__ __forceinline__ void eval_random_access(const GateDesc& g, const u64*
   }
   for (u32 i = 0; i < extra; i++) e.emit(fsub(K(i), W((2 + vs) * copies + i)));
 }
-template <class M>
-__device__ __forceinline__ void eval_u32_arithmetic(const GateDesc& g, const u64* w, Emitter<M>& e) {  // arithmetic_u32.rs:326-386
+template <class E>
+__device__ __forceinline__ void eval_u32_arithmetic(const GateDesc& g, const u64* w, E& e) {  // arithmetic_u32.rs:326-386
   const u32 ops = g.p0;
   for (u32 i = 0; i < ops; i++) {
     u64 m0 = W(6 * i), m1 = W(6 * i + 1), add = W(6 * i + 2), lo = W(6 * i + 3), hi = W(6 * i + 4), inverse = W(6 * i + 5);
@@ -198,8 +205,8 @@ __device__ __forceinline__ void eval_u32_arithmetic(const GateDesc& g, const u64
     e.emit(fsub(ch, hi));
   }
 }
-template <class M>
-__device__ __forceinline__ void eval_u32_add_many(const GateDesc& g, const u64* w, Emitter<M>& e) {  // add_many_u32.rs:143-184
+template <class E>
+__device__ __forceinline__ void eval_u32_add_many(const GateDesc& g, const u64* w, E& e) {  // add_many_u32.rs:143-184
   const u32 na = g.p0, ops = g.p1;
   for (u32 i = 0; i < ops; i++) {
     const u32 b = (na + 3) * i;
@@ -219,8 +226,8 @@ __device__ __forceinline__ void eval_u32_add_many(const GateDesc& g, const u64* 
     e.emit(fsub(cc, oc));
   }
 }
-template <class M>
-__device__ __forceinline__ void eval_u32_range_check(const GateDesc& g, const u64* w, Emitter<M>& e) {  // range_check_u32.rs:89-111
+template <class E>
+__device__ __forceinline__ void eval_u32_range_check(const GateDesc& g, const u64* w, E& e) {  // range_check_u32.rs:89-111
   const u32 n = g.p0;
   for (u32 i = 0; i < n; i++) {
     u64 sum = 0;
@@ -229,8 +236,8 @@ __device__ __forceinline__ void eval_u32_range_check(const GateDesc& g, const u6
     for (u32 j = 0; j < 16; j++) e.emit(e.range_product(W(n + 16 * i + j), 4));
   }
 }
-template <class M>
-__device__ __forceinline__ void eval_u32_subtraction(const GateDesc& g, const u64* w, Emitter<M>& e) {  // subtraction_u32.rs:233-271
+template <class E>
+__device__ __forceinline__ void eval_u32_subtraction(const GateDesc& g, const u64* w, E& e) {  // subtraction_u32.rs:233-271
   const u32 ops = g.p0;
   for (u32 i = 0; i < ops; i++) {
     u64 x = W(5 * i), y = W(5 * i + 1), br = W(5 * i + 2), res = W(5 * i + 3), ob = W(5 * i + 4);
@@ -246,8 +253,8 @@ __device__ __forceinline__ void eval_u32_subtraction(const GateDesc& g, const u6
     e.emit(e.mul(ob, fsub(1, ob)));
   }
 }
-template <class M>
-__device__ __forceinline__ void eval_comparison(const GateDesc& g, const u64* w, Emitter<M>& e) {  // comparison.rs:325-402
+template <class E>
+__device__ __forceinline__ void eval_comparison(const GateDesc& g, const u64* w, E& e) {  // comparison.rs:325-402
   const u32 nc = g.p1, cb = (g.p0 + g.p1 - 1) / g.p1;
   u64 fcomb = 0, scomb = 0;
   for (u32 i = nc; i-- > 0;) {
@@ -285,34 +292,34 @@ struct X2 {
 #define WX(k) X2{W(k), W((k) + 1)}
 __device__ __forceinline__ X2 xadd(X2 x, X2 y) { return X2{fadd(x.a, y.a), fadd(x.b, y.b)}; }
 __device__ __forceinline__ X2 xsub(X2 x, X2 y) { return X2{fsub(x.a, y.a), fsub(x.b, y.b)}; }
-template <class M>
-__device__ __forceinline__ X2 xmul(X2 x, X2 y, Emitter<M>& e) {
+template <class E>
+__device__ __forceinline__ X2 xmul(X2 x, X2 y, E& e) {
   u64 t = e.mul(x.b, y.b);
   return X2{e.mul_add(x.a, y.a, e.mul(7, t)), e.mul_add(x.a, y.b, e.mul(x.b, y.a))};
 }
-template <class M>
-__device__ __forceinline__ X2 xscale(X2 x, u64 s, Emitter<M>& e) { return X2{e.mul(x.a, s), e.mul(x.b, s)}; }
-template <class M>
-__device__ __forceinline__ void emit2(X2 v, Emitter<M>& e) {  // yield_constr.many(x.to_basefield_array())
+template <class E>
+__device__ __forceinline__ X2 xscale(X2 x, u64 s, E& e) { return X2{e.mul(x.a, s), e.mul(x.b, s)}; }
+template <class E>
+__device__ __forceinline__ void emit2(X2 v, E& e) {  // yield_constr.many(x.to_basefield_array())
   e.emit(v.a);
   e.emit(v.b);
 }
-template <class M>
-__device__ __forceinline__ void eval_arithmetic_ext(const GateDesc& g, const u64* w, const u64* kc, Emitter<M>& e) {  // arithmetic_extension.rs:129-147
+template <class E>
+__device__ __forceinline__ void eval_arithmetic_ext(const GateDesc& g, const u64* w, const u64* kc, E& e) {  // arithmetic_extension.rs:129-147
   const u64 c0 = K(0), c1 = K(1);
   for (u32 i = 0; i < g.p0; i++) {
     X2 computed = xadd(xscale(xmul(WX(8 * i), WX(8 * i + 2), e), c0, e), xscale(WX(8 * i + 4), c1, e));
     emit2(xsub(WX(8 * i + 6), computed), e);
   }
 }
-template <class M>
-__device__ __forceinline__ void eval_mul_ext(const GateDesc& g, const u64* w, const u64* kc, Emitter<M>& e) {  // multiplication_extension.rs:122-137
+template <class E>
+__device__ __forceinline__ void eval_mul_ext(const GateDesc& g, const u64* w, const u64* kc, E& e) {  // multiplication_extension.rs:122-137
   const u64 c0 = K(0);
   for (u32 i = 0; i < g.p0; i++) emit2(xsub(WX(6 * i + 4), xscale(xmul(WX(6 * i), WX(6 * i + 2), e), c0, e)), e);
 }
 // reducing.rs:160-180 (EXT = false: base-field coefficients, one wire each) / reducing_extension.rs:160-179 (EXT = true)
-template <bool EXT, class M>
-__device__ __forceinline__ void eval_reducing(const GateDesc& g, const u64* w, Emitter<M>& e) {
+template <bool EXT, class E>
+__device__ __forceinline__ void eval_reducing(const GateDesc& g, const u64* w, E& e) {
   const u32 n = g.p0, cw = EXT ? 2 : 1, start_accs = 6 + cw * n;
   const X2 alpha = WX(2);
   X2 acc = WX(4);
@@ -323,8 +330,8 @@ __device__ __forceinline__ void eval_reducing(const GateDesc& g, const u64* w, E
     acc = a;
   }
 }
-template <class M>
-__device__ __forceinline__ void eval_exponentiation(const GateDesc& g, const u64* w, Emitter<M>& e) {  // exponentiation.rs:266-299
+template <class E>
+__device__ __forceinline__ void eval_exponentiation(const GateDesc& g, const u64* w, E& e) {  // exponentiation.rs:266-299
   const u32 nb = g.p0;
   const u64 base = W(0);
   u64 prev_inter = 0;
@@ -337,8 +344,8 @@ __device__ __forceinline__ void eval_exponentiation(const GateDesc& g, const u64
   }
   e.emit(fsub(W(1 + nb), prev_inter));
 }
-template <class M>
-__device__ __forceinline__ void eval_poseidon_mds(const u64* w, Emitter<M>& e) {  // poseidon_mds.rs:184-203
+template <class E>
+__device__ __forceinline__ void eval_poseidon_mds(const u64* w, E& e) {  // poseidon_mds.rs:184-203
   for (u32 r = 0; r < 12; r++) {
     X2 acc{0, 0};
 #pragma unroll
@@ -355,8 +362,8 @@ __device__ __forceinline__ void eval_poseidon_mds(const u64* w, Emitter<M>& e) {
   }
 }
 // gates/interpolation.rs:21-76 layout: shift 0 | values 1.. | evaluation point | evaluation value | coefficients
-template <class M>
-__device__ __forceinline__ void eval_high_degree_interpolation(const GateDesc& g, const u64* w, const u64* roots, Emitter<M>& e) {  // high_degree_interpolation.rs:126-147
+template <class E>
+__device__ __forceinline__ void eval_high_degree_interpolation(const GateDesc& g, const u64* w, const u64* roots, E& e) {  // high_degree_interpolation.rs:126-147
   const u32 np = 1u << g.p0, ep_w = 1 + 2 * np, ev_w = ep_w + 2, coeffs_w = ev_w + 2;
   const u64 gen = roots[g.p0];
   u64 point = W(0);
@@ -371,8 +378,8 @@ __device__ __forceinline__ void eval_high_degree_interpolation(const GateDesc& g
   for (u32 k = np; k-- > 0;) acc = xadd(xmul(acc, ep, e), WX(coeffs_w + 2 * k));
   emit2(xsub(WX(ev_w), acc), e);
 }
-template <class M>
-__device__ __forceinline__ void eval_low_degree_interpolation(const GateDesc& g, const u64* w, const u64* roots, Emitter<M>& e) {  // low_degree_interpolation.rs:356-404
+template <class E>
+__device__ __forceinline__ void eval_low_degree_interpolation(const GateDesc& g, const u64* w, const u64* roots, E& e) {  // low_degree_interpolation.rs:356-404
   const u32 np = 1u << g.p0, ep_w = 1 + 2 * np, ev_w = ep_w + 2, coeffs_w = ev_w + 2, end_coeffs = coeffs_w + 2 * np;
   auto shift_pow_w = [&](u32 i) { return i == 1 ? 0u : end_coeffs + i - 2; };                     // :50-57
   auto eval_pow_w = [&](u32 i) { return i == 1 ? ep_w : end_coeffs + np - 2 + 2 * (i - 2); };     // :59-67
@@ -397,8 +404,8 @@ __device__ __forceinline__ void eval_low_degree_interpolation(const GateDesc& g,
   emit2(xsub(WX(ev_w), acc), e);
 }
 // gates/poseidon.rs:485-564
-template <class M>
-__device__ __forceinline__ void eval_poseidon(const u64* w, Emitter<M>& e) {
+template <class E>
+__device__ __forceinline__ void eval_poseidon(const u64* w, E& e) {
   constexpr u32 SWAP = 24, DELTA = 25, FULL0 = 29, PARTIAL = 29 + 36, FULL1 = 29 + 36 + 22;
   u64 swap = W(SWAP);
   e.emit(e.mul(swap, fsub(swap, 1)));
@@ -483,123 +490,178 @@ __device__ __forceinline__ void eval_poseidon(const u64* w, Emitter<M>& e) {
 // field inverse by Fermat (the reference uses a binary GCD, field/src/inversion.rs; the value is the same)
 __device__ __forceinline__ u64 finv(u64 a) { return gl::pow(a, gl::P - 2); }
 
-// All terms of one LDE point folded into acc[c] = sum_t alpha_c^t * term_t (before the division by Z_H).
-template <class M>
-__device__ __forceinline__ void eval_point(const Params& p, const u64 i, const u64 lde_size, M& mode, u64 (&acc)[MAX_CHALLENGES]) {
+// One thread evaluates PPT points, gate by gate: for every gate the PPT points run through the same evaluator code
+// back to back, so the instruction stream of a gate (the kernel is ~300 KB of SASS) is fetched once per PPT points instead
+// of once per point -- instruction-cache misses were the top stall (profiles/r01_quotient.md).  The per-point partial
+// sums live in shared memory: acc[(c * PPT + k) * blockDim + tid].
+struct PointRows {
+  const u64 *w, *cs, *zp, *zn;
+  u64 x;
+};
+__device__ __forceinline__ PointRows point_rows(const Params& p, const u64 i, const u64 lde_size, bool with_x) {
   const u32 lde_bits = p.degree_bits + p.rate_bits;
   const u32 step_log = p.rate_bits - p.qdb;
   const u64 row = lde_bits ? (__brevll(i << step_log) >> (64 - lde_bits)) : 0;
   const u64 i_next = (i + ((u64)1 << p.qdb)) & (lde_size - 1);
   const u64 row_next = lde_bits ? (__brevll(i_next << step_log) >> (64 - lde_bits)) : 0;
-  const u64* w = p.wires + row * p.wires_stride;
-  const u64* cs = p.cs + row * p.cs_stride;
-  const u64* zp = p.zs_pp + row * p.zs_stride;
-  const u64* zn = p.zs_pp + row_next * p.zs_stride;
-  const u32 nc = p.num_challenges, nr = p.num_routed, npp = p.num_partial_products, md = p.max_degree;
+  PointRows r;
+  r.w = p.wires + row * p.wires_stride;
+  r.cs = p.cs + row * p.cs_stride;
+  r.zp = p.zs_pp + row * p.zs_stride;
+  r.zn = p.zs_pp + row_next * p.zs_stride;
+  r.x = with_x ? gl::mul(7, gl::pow(p.w, i)) : 0;  // shifted_x = coset_shift * w^i (prover.rs:907)
+  return r;
+}
+
+// vanishing_z_1_terms and partial-product checks (vanishing_poly.rs:160-205) of one point.
+// reduce_with_powers_multi reduces ONE term list [z1 terms of every challenge | pp checks of every challenge |
+// gate constraints] with each alpha, so the terms produced for challenge tc enter every challenge c's sum.
+template <class M, int NC>
+__device__ __forceinline__ void eval_permutation_terms(const Params& p, const u64 i, const u64 lde_size, M& mode, u64 (&acc)[NC]) {
+  const PointRows r = point_rows(p, i, lde_size, true);
+  const u64 *w = r.w, *cs = r.cs, *zp = r.zp, *zn = r.zn;
+  const u64 x = r.x;
+  const u32 nr = p.num_routed, npp = p.num_partial_products, md = p.max_degree;
   const u32 rate_mask = (1u << p.qdb) - 1;
   auto fm = [&](u64 a, u64 b) { return gl::mul(a, b, mode); };
   auto fma = [&](u64 a, u64 b, u64 c) { return gl::mul_add(a, b, c, mode); };
-
-  const u64 x = gl::mul(7, gl::pow(p.w, i));  // shifted_x = coset_shift * w^i (prover.rs:907)
 #pragma unroll
-  for (int c = 0; c < MAX_CHALLENGES; c++) acc[c] = 0;
-
-  // ---- vanishing_z_1_terms and partial-product checks (vanishing_poly.rs:160-205) ----
-  // reduce_with_powers_multi reduces ONE term list [z1 terms of every challenge | pp checks of every challenge |
-  // gate constraints] with each alpha, so the terms produced for challenge tc enter every challenge c's sum.
-  {
-    // eval_l_0 (zero_poly_coset.rs:57-60)
-    const u64 l0 = gl::mul(p.zh[i & rate_mask], finv(gl::mul(p.n_field, gl::sub(x, 1))));
-    const u32 chunks = npp + 1;
-    for (u32 tc = 0; tc < nc; tc++) {
-      const u64 z_x = __ldg(zp + tc), z_gx = __ldg(zn + tc);
-      const u64 t_z1 = fm(l0, gl::sub(z_x, 1));
-      for (u32 c = 0; c < nc; c++) acc[c] = fma(t_z1, __ldg(p.alpha_pows + (u64)c * p.num_terms + tc), acc[c]);
-      const u64 beta = p.betas[tc], gamma = p.gammas[tc];
-      const u64 bx = fm(beta, x);
-      u64 prev = z_x;
-      for (u32 ch = 0; ch < chunks; ch++) {
-        u64 num = 1, den = 1;
-        const u32 j1 = min(nr, (ch + 1) * md);
-        for (u32 j = ch * md; j < j1; j++) {
-          const u64 wv = __ldg(w + j);
-          num = fm(num, gl::add(gl::add(wv, fm(bx, __ldg(p.k_is + j))), gamma));                    // :175-181
-          den = fm(den, gl::add(gl::add(wv, fm(beta, __ldg(cs + p.num_constants + j))), gamma));     // :182-186
-        }
-        const u64 next = ch + 1 < chunks ? __ldg(zp + nc + tc * npp + ch) : z_gx;
-        const u64 term = gl::sub(fm(prev, num), fm(next, den));  // partial_products.rs:70-75
-        for (u32 c = 0; c < nc; c++)
-          acc[c] = fma(term, __ldg(p.alpha_pows + (u64)c * p.num_terms + nc + tc * chunks + ch), acc[c]);
-        prev = next;
+  for (int c = 0; c < NC; c++) acc[c] = 0;
+  // eval_l_0 (zero_poly_coset.rs:57-60)
+  const u64 l0 = gl::mul(p.zh[i & rate_mask], finv(gl::mul(p.n_field, gl::sub(x, 1))));
+  const u32 chunks = npp + 1;
+#pragma unroll 1
+  for (u32 tc = 0; tc < (u32)NC; tc++) {
+    const u64 z_x = __ldg(zp + tc), z_gx = __ldg(zn + tc);
+    const u64 t_z1 = fm(l0, gl::sub(z_x, 1));
+#pragma unroll
+    for (int c = 0; c < NC; c++) acc[c] = fma(t_z1, __ldg(p.alpha_pows + (u64)c * p.num_terms + tc), acc[c]);
+    const u64 beta = p.betas[tc], gamma = p.gammas[tc];
+    const u64 bx = fm(beta, x);
+    u64 prev = z_x;
+    for (u32 ch = 0; ch < chunks; ch++) {
+      u64 num = 1, den = 1;
+      const u32 j1 = min(nr, (ch + 1) * md);
+      for (u32 j = ch * md; j < j1; j++) {
+        const u64 wv = __ldg(w + j);
+        num = fm(num, gl::add(gl::add(wv, fm(bx, __ldg(p.k_is + j))), gamma));                    // :175-181
+        den = fm(den, gl::add(gl::add(wv, fm(beta, __ldg(cs + p.num_constants + j))), gamma));     // :182-186
       }
-    }
-  }
-
-  // ---- gate constraints (vanishing_poly.rs:267-306) ----
-  const u32 gate_base = nc * (npp + 2);
-  const u64* kc = cs + p.num_selectors;  // vars.remove_prefix(num_selectors), gate.rs:138
-  for (u32 gi = 0; gi < p.num_gates; gi++) {
-    const GateDesc g = p.gates[gi];
-    // compute_filter (gate.rs:261-268)
-    const u64 s = __ldg(cs + g.selector_index);
-    u64 filter = 1;
-    for (u32 k = g.group_start; k < g.group_end; k++)
-      if (k != gi) filter = fm(filter, gl::sub((u64)k, s));
-    if (p.num_selectors > 1) filter = fm(filter, gl::sub(0xFFFFFFFFull, s));
-    Emitter<M> e(mode);
-    e.init(p.alpha_pows, p.num_terms, gate_base, nc);
-    switch (g.type) {
-      case G_NOOP: break;
-      case G_CONSTANT: eval_constant(g, w, kc, e); break;
-      case G_PUBLIC_INPUT: eval_public_input(w, p.pih, e); break;
-      case G_ARITHMETIC: eval_arithmetic(g, w, kc, e); break;
-      case G_BASE_SUM: eval_base_sum(g, w, e); break;
-      case G_POSEIDON: eval_poseidon(w, e); break;
-      case G_RANDOM_ACCESS: eval_random_access(g, w, kc, e); break;
-      case G_U32_ARITHMETIC: eval_u32_arithmetic(g, w, e); break;
-      case G_U32_ADD_MANY: eval_u32_add_many(g, w, e); break;
-      case G_U32_RANGE_CHECK: eval_u32_range_check(g, w, e); break;
-      case G_U32_SUBTRACTION: eval_u32_subtraction(g, w, e); break;
-      case G_COMPARISON: eval_comparison(g, w, e); break;
-      case G_ARITHMETIC_EXT: eval_arithmetic_ext(g, w, kc, e); break;
-      case G_MUL_EXT: eval_mul_ext(g, w, kc, e); break;
-      case G_REDUCING: eval_reducing<false>(g, w, e); break;
-      case G_REDUCING_EXT: eval_reducing<true>(g, w, e); break;
-      case G_EXPONENTIATION: eval_exponentiation(g, w, e); break;
-      case G_POSEIDON_MDS: eval_poseidon_mds(w, e); break;
-      case G_HIGH_DEGREE_INTERPOLATION: eval_high_degree_interpolation(g, w, p.small_roots, e); break;
-      case G_LOW_DEGREE_INTERPOLATION: eval_low_degree_interpolation(g, w, p.small_roots, e); break;
-      default: break;
-    }
+      const u64 next = ch + 1 < chunks ? __ldg(zp + NC + tc * npp + ch) : z_gx;
+      const u64 term = gl::sub(fm(prev, num), fm(next, den));  // partial_products.rs:70-75
 #pragma unroll
-    for (int c = 0; c < MAX_CHALLENGES; c++)
-      if ((u32)c < nc) acc[c] = fma(filter, e.acc[c], acc[c]);
+      for (int c = 0; c < NC; c++)
+        acc[c] = fma(term, __ldg(p.alpha_pows + (u64)c * p.num_terms + NC + tc * chunks + ch), acc[c]);
+      prev = next;
+    }
   }
 }
 
-__global__ void __launch_bounds__(128) quotient_values_kernel(Params p) {
+// filter_g * sum_j alpha_c^(gate_base + j) c_{g,j} of one gate at one point (vanishing_poly.rs:267-306)
+template <class M, int NC>
+__device__ __forceinline__ void eval_gate_terms(const Params& p, const GateDesc& g, const u32 gi, const u64 i, const u64 lde_size,
+                                                M& mode, u64 (&out)[NC]) {
+  const PointRows r = point_rows(p, i, lde_size, false);
+  const u64 *w = r.w, *cs = r.cs;
+  const u64* kc = cs + p.num_selectors;  // vars.remove_prefix(num_selectors), gate.rs:138
+  auto fm = [&](u64 a, u64 b) { return gl::mul(a, b, mode); };
+  // compute_filter (gate.rs:261-268)
+  const u64 s = __ldg(cs + g.selector_index);
+  u64 filter = 1;
+  for (u32 k = g.group_start; k < g.group_end; k++)
+    if (k != gi) filter = fm(filter, gl::sub((u64)k, s));
+  if (p.num_selectors > 1) filter = fm(filter, gl::sub(0xFFFFFFFFull, s));
+  Emitter<M, NC> e(mode);
+  e.init(p.alpha_pows, p.num_terms, NC * (p.num_partial_products + 2));
+  switch (g.type) {
+    case G_NOOP: break;
+    case G_CONSTANT: eval_constant(g, w, kc, e); break;
+    case G_PUBLIC_INPUT: eval_public_input(w, p.pih, e); break;
+    case G_ARITHMETIC: eval_arithmetic(g, w, kc, e); break;
+    case G_BASE_SUM: eval_base_sum(g, w, e); break;
+    case G_POSEIDON: eval_poseidon(w, e); break;
+    case G_RANDOM_ACCESS: eval_random_access(g, w, kc, e); break;
+    case G_U32_ARITHMETIC: eval_u32_arithmetic(g, w, e); break;
+    case G_U32_ADD_MANY: eval_u32_add_many(g, w, e); break;
+    case G_U32_RANGE_CHECK: eval_u32_range_check(g, w, e); break;
+    case G_U32_SUBTRACTION: eval_u32_subtraction(g, w, e); break;
+    case G_COMPARISON: eval_comparison(g, w, e); break;
+    case G_ARITHMETIC_EXT: eval_arithmetic_ext(g, w, kc, e); break;
+    case G_MUL_EXT: eval_mul_ext(g, w, kc, e); break;
+    case G_REDUCING: eval_reducing<false>(g, w, e); break;
+    case G_REDUCING_EXT: eval_reducing<true>(g, w, e); break;
+    case G_EXPONENTIATION: eval_exponentiation(g, w, e); break;
+    case G_POSEIDON_MDS: eval_poseidon_mds(w, e); break;
+    case G_HIGH_DEGREE_INTERPOLATION: eval_high_degree_interpolation(g, w, p.small_roots, e); break;
+    case G_LOW_DEGREE_INTERPOLATION: eval_low_degree_interpolation(g, w, p.small_roots, e); break;
+    default: break;
+  }
+#pragma unroll
+  for (int c = 0; c < NC; c++) out[c] = fm(filter, e.result(c));
+}
+
+// the PPT points of this thread: i_k = first + k * blockDim.x
+template <class M, int NC, int PPT>
+__device__ __forceinline__ void eval_batch(const Params& p, const u64 first, const u64 lde_size, M& mode, u64* __restrict__ sh) {
+  const u32 bd = blockDim.x;
+#pragma unroll 1
+  for (int k = 0; k < PPT; k++) {
+    const u64 i = first + (u64)k * bd;
+    if (i >= lde_size) break;
+    u64 a[NC];
+    eval_permutation_terms(p, i, lde_size, mode, a);
+#pragma unroll
+    for (int c = 0; c < NC; c++) sh[(c * PPT + k) * bd] = a[c];
+  }
+#pragma unroll 1
+  for (u32 gi = 0; gi < p.num_gates; gi++) {
+    const GateDesc g = p.gates[gi];
+    if (g.type == G_NOOP) continue;
+#pragma unroll 1
+    for (int k = 0; k < PPT; k++) {
+      const u64 i = first + (u64)k * bd;
+      if (i >= lde_size) break;
+      u64 t[NC];
+      eval_gate_terms(p, g, gi, i, lde_size, mode, t);
+#pragma unroll
+      for (int c = 0; c < NC; c++) sh[(c * PPT + k) * bd] = gl::add(sh[(c * PPT + k) * bd], t[c]);
+    }
+    // keep the CTA's warps on the same gate: they then share the instruction-cache lines of that gate's evaluator
+    __syncthreads();
+  }
+}
+
+#ifndef P2B_QUOT_BLOCK
+#define P2B_QUOT_BLOCK 512
+#endif
+template <int NC, int PPT>
+__global__ void __launch_bounds__(P2B_QUOT_BLOCK) quotient_values_kernel(Params p) {
+  extern __shared__ u64 qsh[];  // [NC][PPT][blockDim]
   const u64 lde_size = (u64)1 << (p.degree_bits + p.qdb);
-  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= lde_size) return;
-  u64 acc[MAX_CHALLENGES];
+  const u64 first = (u64)blockIdx.x * blockDim.x * PPT + threadIdx.x;  // may lie beyond the domain: such threads only keep the barriers
+  u64* sh = qsh + threadIdx.x;
 #ifndef P2B_EXACT_ONLY
   gl::Optimistic fast;
-  eval_point(p, i, lde_size, fast, acc);
-  if (fast.rare)  // an optimistic reduction hit its rare case somewhere in this point: redo the point exactly
+  eval_batch<gl::Optimistic, NC, PPT>(p, first, lde_size, fast, sh);
+  // an optimistic reduction hit its rare case somewhere in this CTA's points: redo them exactly (CTA-wide decision: the
+  // evaluation contains barriers)
+  if (__syncthreads_or(fast.rare))
 #endif
   {
     gl::Exact exact;
-    eval_point(p, i, lde_size, exact, acc);
+    eval_batch<gl::Exact, NC, PPT>(p, first, lde_size, exact, sh);
   }
   // ---- divide by Z_H (prover.rs:985-991) ----
-  const u32 nc = p.num_challenges;
-  const u64 zi = p.zh_inv[i & ((1u << p.qdb) - 1)];
+#pragma unroll 1
+  for (int k = 0; k < PPT; k++) {
+    const u64 i = first + (u64)k * blockDim.x;
+    if (i >= lde_size) break;
+    const u64 zi = p.zh_inv[i & ((1u << p.qdb) - 1)];
 #pragma unroll
-  for (int c = 0; c < MAX_CHALLENGES; c++) {
-    if ((u32)c < nc) {
-      const u64 v = gl::canon(gl::mul(acc[c], zi));
+    for (int c = 0; c < NC; c++) {
+      const u64 v = gl::canon(gl::mul(sh[(c * PPT + k) * blockDim.x], zi));
       p.out_values[(u64)c * lde_size + i] = v;
-      if (p.out_rows) p.out_rows[i * nc + c] = v;
+      if (p.out_rows) p.out_rows[i * NC + c] = v;
     }
   }
 }
