@@ -311,7 +311,8 @@ def run_b200(args, rank, world, local_rank):
             "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": "PolynomialBatch::from_values 2^%d x %d Goldilocks, rate_bits 3, cap_height 4, Poseidon Merkle "
-                                   "(BASELINE.json configs[1])" % (n_log, P),
+                                   "(%s)" % (n_log, P, "BASELINE.json configs[1]" if (n_log, P) == (20, 135)
+                                             else "BASELINE.json configs[4] scale sweep: NOT the headline size the metric name quotes"),
                        "sharding": "columns for iNTT, coset blocks / cap sub-trees for LDE+Merkle" if world > 1 else "single GPU",
                        "l2": "inputs_exceed_l2 (values %.2f GB, LDE %.2f GB per step vs 126 MB L2)" % (P * n * 8 / 1e9, P * N * 8 / 1e9),
                        "timing": "CUDA events on the library stream around all steps, max over ranks; wall %.1f ms/step" % (wall_ms / args.steps),
