@@ -16,6 +16,13 @@ int main() {
     std::vector<std::vector<F>> vals(3, std::vector<F>(8, 1));
     PolynomialBatch b = PolynomialBatch::from_values(ctx, vals, 1, false, 0);
     MerkleCap cap = b.merkle_tree.cap();
+    // the FRI-facing mirror: openings and prove_openings over the same batch
+    Ext zeta{{5, 7}};
+    std::vector<Ext> op = eval_openings(ctx, b, zeta);
+    Challenger ch;
+    FriBatchInfo fb{zeta, {{0, 0}, {0, 1}, {0, 2}}};
+    FriProof pr = prove_openings(ctx, {&b}, {fb}, ch, 3, 1, 0, 2, 3, {1});
+    if (pr.query_round_proofs.size() != 3 || pr.final_poly.size() != 4 || op.size() != 3) return 4;
     std::printf("cap %llu\n", (unsigned long long)cap.hashes[0].elements[0]);
   } catch (const std::exception& e) { std::printf("ERR %s\n", e.what()); return 3; }
   return 0;
