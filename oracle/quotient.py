@@ -11,12 +11,13 @@ quotient-polynomial evaluation over the LDE domain:
 and of the gates' constraint polynomials (each class cites its file).
 
 Written from the Rust sources, independently of the CUDA kernels (different language, no shared code), for small
-circuits.  Parity pinning: the reference stores no vectors for quotient values ("parity unpinned" by stored vectors);
-the restatement is pinned by the reference's own property tests restated in tests/test_quotient_oracle.py -- every
-gate's constraints vanish on a witness row produced by that gate's generator logic and do not on a corrupted one
-(gate_testing.rs), Poseidon-gate rows are produced by the KAT-pinned permutation, and the quotient of an honest
-witness has degree < (quotient_degree_factor - 1) * n + ... (top coefficients zero), which exercises filters, the
-permutation argument, L_0, the alpha reduction order and the division by Z_H together.
+circuits.  Parity pinning: the reference stores no vectors for quotient values; this restatement is pinned by the
+reference ITSELF run on the GPU box (oracle/_ref = the reference's CUDA translation unit compiled unmodified):
+tests/test_ref_cuda_crosscheck.py checks every base gate type against the reference's device-side evaluators
+(cuda/*Gate.cuh) and the full quotient values against the reference's compute_quotient_values_kernel on its own 25-gate
+circuit.  In addition tests/test_quotient_oracle.py restates the reference's property tests -- every gate's constraints
+vanish on a witness row produced by that gate's generator logic and do not on a corrupted one (gate_testing.rs), and the
+quotient of an honest witness has its top coefficients zero.
 """
 from . import poseidon_params as PP
 

@@ -123,3 +123,107 @@ def test_compat_build_merkle_tree_and_transpose(env):
     assert np.array_equal(base.to_host(N * Pn).reshape(N, Pn), exp.leaves)
     assert np.array_equal(base.to_host(4 * nd, offset=2 * pad).reshape(nd, 4), exp.digests)
     assert np.array_equal(base.to_host(4 * ncap, offset=2 * pad + 4 * nd).reshape(ncap, 4), exp.cap)
+
+
+# ---- gate constraints: the reference's own device-side evaluators (cuda/*Gate.cuh) vs the oracle's restatement -------
+def _gate_cases():
+    from oracle import quotient as Q
+    return [Q.NoopGate(), Q.ConstantGate(2), Q.PublicInputGate(), Q.ArithmeticGate(20), Q.BaseSumGate(63, 2), Q.BaseSumGate(16, 4),
+            Q.PoseidonGate(), Q.RandomAccessGate(4, 4, 2), Q.RandomAccessGate(2, 13, 2), Q.U32ArithmeticGate(6), Q.U32AddManyGate(3, 9),
+            Q.U32AddManyGate(11, 5), Q.U32RangeCheckGate(8), Q.U32RangeCheckGate(1), Q.U32SubtractionGate(11), Q.ComparisonGate(32, 16),
+            Q.ComparisonGate(8, 4)]
+
+
+@pytest.mark.parametrize("gate", _gate_cases(), ids=lambda g: type(g).__name__ + str(g.params))
+def test_gate_constraints_match_reference_cuda_gates(env, gate):
+    """Pins oracle/quotient.py's gate restatements to the reference's code: same rows through cuda/<Gate>.cuh's
+    eval_unfiltered_base_packed (instantiated like cuda/plonky2_gpu_impl.cuh:633-685) and through the oracle."""
+    from tests import quotient_fixtures as F
+    ctx, ref, streams, _ = env
+    ref.p2ref_eval_gate.restype = C.c_int
+    ref.p2ref_eval_gate.argtypes = [C.c_int] * 4 + [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    rng = np.random.default_rng(5)
+    nw, ncst, rows = 234, 4, 24
+    pih = [int(x) for x in rng.integers(0, P_, size=4, dtype=np.uint64)]
+    wires = np.zeros((rows, nw), dtype=np.uint64)
+    consts = np.zeros((rows, ncst), dtype=np.uint64)
+    for r in range(rows):
+        gc = [int(x) for x in rng.integers(0, P_, size=ncst, dtype=np.uint64)]
+        if r % 2 == 0:      # a row the gate's generator would write (most constraints vanish) ...
+            wires[r] = np.array(F.honest_row(gate, rng, nw, gc, pih), dtype=np.uint64)
+        else:               # ... and arbitrary field elements (every constraint exercised with non-trivial values)
+            wires[r] = rng.integers(0, P_, size=nw, dtype=np.uint64)
+        consts[r] = np.array(gc, dtype=np.uint64)
+    nout = max(gate.num_constraints(), 1)
+    dw, dk = p2b.DeviceBuffer.from_host(ctx, wires.reshape(-1)), p2b.DeviceBuffer.from_host(ctx, consts.reshape(-1))
+    dp = p2b.DeviceBuffer.from_host(ctx, np.array(pih, dtype=np.uint64))
+    do = p2b.DeviceBuffer(ctx, rows * nout)
+    ctx.synchronize()
+    params = list(gate.params) + [0, 0, 0]
+    rc = ref.p2ref_eval_gate(gate.type_id, params[0], params[1], params[2], dw.ptr, nw, dk.ptr, ncst, dp.ptr, do.ptr, nout, rows)
+    assert rc == 0
+    got = canon(do.to_host().reshape(rows, nout))[:, :gate.num_constraints()]
+    for r in range(rows):
+        want = gate.eval_unfiltered([int(x) for x in consts[r]], [int(x) for x in wires[r]], pih)
+        assert [int(x) for x in got[r]] == want, "row %d" % r
+
+
+# ---- quotient values: the reference's own kernel (hard-wired to its 25-gate circuit) vs the oracle vs this library ----
+def _reference_circuit(degree_bits):
+    """The circuit cuda/plonky2_gpu_impl.cuh:596-685 is compiled for: 25 gate instances, 6 selector groups."""
+    from oracle import quotient as Q
+    gates = [Q.NoopGate(), Q.ConstantGate(2), Q.PublicInputGate(), Q.BaseSumGate(32, 2), Q.BaseSumGate(63, 2), Q.ArithmeticGate(20),
+             Q.BaseSumGate(16, 4), Q.ComparisonGate(32, 16), Q.U32AddManyGate(0, 11), Q.U32AddManyGate(11, 5), Q.U32AddManyGate(13, 5),
+             Q.U32AddManyGate(15, 4), Q.U32AddManyGate(16, 4), Q.U32AddManyGate(2, 10), Q.U32AddManyGate(3, 9), Q.U32AddManyGate(5, 9),
+             Q.U32AddManyGate(7, 8), Q.U32AddManyGate(9, 6), Q.U32ArithmeticGate(6), Q.U32RangeCheckGate(0), Q.U32RangeCheckGate(1),
+             Q.U32RangeCheckGate(8), Q.U32SubtractionGate(11), Q.RandomAccessGate(4, 4, 2), Q.PoseidonGate()]
+    sel = [0] * 6 + [1] * 5 + [2] * 5 + [3] * 5 + [4] * 3 + [5]
+    groups = [(0, 6), (6, 11), (11, 16), (16, 21), (21, 24), (24, 25)]
+    k_is = [pow(7, j, P_) for j in range(80)]
+    circ = Q.Circuit(gates, sel, groups, 234, 80, 8, k_is, degree_bits, 3, 2, 8)
+    assert circ.num_gate_constraints == 231          # the constant the reference kernel asserts (plonky2_gpu_impl.cuh:512-514)
+    return circ
+
+
+def test_quotient_values_match_reference_cuda_kernel(env):
+    """compute_quotient_values_kernel (cuda/plonky2_gpu_impl.cuh:485-876) on random leaves of its own circuit: the oracle's
+    quotient values and this library's quotient kernel reproduce it bit-for-bit -- every gate filter, the permutation
+    argument, L_0, the alpha-reduction order and the division by Z_H are pinned to the reference's code."""
+    from oracle import quotient as Q
+    ctx, ref, streams, _ = env
+    degree_bits = 4
+    circ = _reference_circuit(degree_bits)
+    N = 1 << (degree_bits + 3)
+    rng = np.random.default_rng(77)
+    rnd = lambda shape: rng.integers(0, P_, size=shape, dtype=np.uint64)
+    wires, zs_pp, cs = rnd((N, 234)), rnd((N, 2 * (1 + circ.num_partial_products))), rnd((N, 8 + 80))
+    cs[:, :6] = rng.integers(0, 25, size=(N, 6), dtype=np.uint64)     # selector columns: small values like real ones
+    pih = [int(x) for x in rnd(4)]
+    alphas, betas, gammas = ([int(x) for x in rnd(2)] for _ in range(3))
+    # the tables the Rust side uploads (fri/oracle.rs + plonk/prover.rs:535-568): points w^i, Z_H on the coset and inverses
+    w = oracle.primitive_root_of_unity(degree_bits + 3)
+    points = np.array([pow(w, i, P_) for i in range(N)], dtype=np.uint64)
+    g_pow_n = pow(7, 1 << degree_bits, P_)
+    v = oracle.primitive_root_of_unity(3)
+    zh = [(g_pow_n * pow(v, i, P_) - 1) % P_ for i in range(8)]
+    zh_inv = [Q.inv(z) for z in zh]
+    dev = lambda a: p2b.DeviceBuffer.from_host(ctx, np.ascontiguousarray(a, dtype=np.uint64).reshape(-1))
+    d_w, d_z, d_c, d_pts = dev(wires), dev(zs_pp), dev(cs), dev(points)
+    d_zh, d_zhi, d_k = dev(np.array(zh, dtype=np.uint64)), dev(np.array(zh_inv, dtype=np.uint64)), dev(np.array(circ.k_is, dtype=np.uint64))
+    d_a, d_b, d_g = (dev(np.array(x, dtype=np.uint64)) for x in (alphas, betas, gammas))
+    d_out = p2b.DeviceBuffer(ctx, 2 * N)
+    ctx.synchronize()
+    ref.p2ref_quotient_values.restype = C.c_int
+    ref.p2ref_quotient_values.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                          C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6
+    rc = ref.p2ref_quotient_values(degree_bits, d_pts.ptr, d_out.ptr, (C.c_uint64 * 4)(*pih), d_c.ptr, 88, d_z.ptr, zs_pp.shape[1], d_w.ptr, 234,
+                                   8, circ.num_partial_products, d_zh.ptr, d_zhi.ptr, d_k.ptr, d_a.ptr, d_b.ptr, d_g.ptr)
+    assert rc == 0
+    ref_vals = canon(d_out.to_host().reshape(N, 2))
+    # oracle
+    want = Q.compute_quotient_values(circ, wires, zs_pp, cs, pih, betas, gammas, alphas)
+    assert [[int(x) for x in r] for r in ref_vals] == [list(r) for r in want]
+    # this library, same rows
+    pc = p2b.Circuit([(g.type_id, g.params) for g in circ.gates], circ.selector_indices, circ.groups, 234, 80, 8, circ.k_is, degree_bits, 3, 2, 8)
+    vals, _ = p2b.compute_quotient_polys_rows(ctx, pc, wires, zs_pp, cs, pih, betas, gammas, alphas)
+    assert np.array_equal(vals.T, ref_vals)
