@@ -80,3 +80,51 @@ def test_wide_ecc_shape_and_quotient_scale(ctx):
     for r, s, i in zip(rows, sibs, idx):
         assert oracle.merkle_verify(r, i, cap, s)
     b.close()
+
+
+def test_full_size_fri_proof_is_accepted_by_the_verifier(ctx):
+    """BASELINE-scale FRI (2^18 x 259 polynomials shaped like the four oracles, standard config: rate 3, cap 4, 16 PoW
+    bits, 28 queries, arity 16): the restated verifier (fri/verifier.rs) accepts the device's proof; a tampered one fails."""
+    from oracle import fri as FR
+    n_log, rate_bits, cap_height, pow_bits, queries = 18, 3, 4, 16, 28
+    polys = (88, 135, 20, 16)
+    n = 1 << n_log
+    arity = FR.constant_arity_bits(4, 5, n_log, rate_bits, cap_height)
+    batches_dev = []
+    for k in polys:
+        d = synth(ctx, k, n)
+        batches_dev.append(p2b.PolynomialBatch.from_values(ctx, (d, k, n), rate_bits, cap_height))
+        del d
+    zeta = (0x123456789abcdef, 0xfedcba987654321)
+    g = oracle.primitive_root_of_unity(n_log)
+    zeta_next = FR.escale(zeta, g)
+    all_polys = [(o, p) for o, k in enumerate(polys) for p in range(k)]
+    batches = [FR.FriBatchInfo(zeta, all_polys), FR.FriBatchInfo(zeta_next, [(2, 0), (2, 1)])]
+    params = FR.FriParams(n_log, rate_bits, cap_height, pow_bits, queries, arity)
+    start = FR.Challenger([3] * 12, [1, 2, 3])
+    gch = p2b.Challenger(start.sponge_state, start.input_buffer, start.output_buffer)
+    proof = p2b.fri_prove_openings(ctx, batches_dev, [(b.point, b.polynomials) for b in batches], gch, n_log, rate_bits, cap_height,
+                                   pow_bits, queries, arity)
+    openings = []
+    for b in batches:
+        per = [p2b.eval_openings(ctx, gb, b.point) for gb in batches_dev]
+        openings.append([tuple(int(x) for x in per[o][p]) for (o, p) in b.polynomials])
+    pr = FR.FriProof()
+    pr.commit_phase_merkle_caps = proof.commit_phase_merkle_caps
+    pr.final_poly = [(int(a), int(c)) for a, c in proof.final_poly]
+    pr.pow_witness = proof.pow_witness
+    pr.query_round_proofs = [([(rows[q], sibs[q]) for rows, sibs in proof.initial], [(ev[q].reshape(-1), sibs[q]) for ev, sibs in proof.steps])
+                             for q in range(queries)]
+    challenges = FR.fri_challenges(start.clone(), pr.commit_phase_merkle_caps, pr.final_poly, pr.pow_witness, params)
+    assert 64 - challenges[2].bit_length() >= pow_bits
+    caps = [gb.cap() for gb in batches_dev]
+    assert FR.verify_fri_proof(batches, (False,) * 4, openings, challenges, caps, pr, params)
+    assert len(pr.final_poly) == 1 << (n_log - sum(arity))
+    # tampering with one opened value breaks the verification
+    bad = list(openings[0])
+    bad[7] = (bad[7][0] ^ 1, bad[7][1])
+    with pytest.raises(AssertionError):
+        FR.verify_fri_proof(batches, (False,) * 4, [bad, openings[1]], challenges, caps, pr, params)
+    proof.close()
+    for gb in batches_dev:
+        gb.close()
