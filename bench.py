@@ -256,6 +256,9 @@ def run_b200(args, rank, world, local_rank):
     hv = host_vals.array.reshape(cmax, n)
     hc = host_coef.array.reshape(cmax, n)
     cap_host = np.empty((1 << CAP_HEIGHT, 4), dtype=np.uint64)
+    copy_stream = torch.cuda.Stream()
+    host_coef_t = torch.from_numpy(host_coef.array.view(np.int64))  # same pinned memory, as torch tensors for the async copies
+    host_vals_t = torch.from_numpy(host_vals.array.view(np.int64)).view(cmax, n)
 
     def step_e2e():
         if world == 1:
@@ -265,18 +268,24 @@ def run_b200(args, rank, world, local_rank):
             b.cap(out=cap_host)                                                       # D2H result (synchronises)
             b.close()
         else:
-            p2b._check(L.p2b_memcpy_h2d(ctx.handle, work.data_ptr(), host_vals.ptr, (c1 - c0) * n * 8))
-            b = sharded.sharded_commit_from_values(engine, comm, work, P, n_log, RATE_BITS, CAP_HEIGHT)
+            def coeffs_to_host(shard):
+                # each rank returns the coefficient columns it transformed, on a side stream while the exchange, the LDE
+                # and the tree run (the single-GPU call does the same inside p2b_commit_from_values_ex)
+                if c1 > c0:
+                    with torch.cuda.stream(copy_stream):
+                        host_coef_t[: (c1 - c0) * n].copy_(shard.view(-1)[: (c1 - c0) * n], non_blocking=True)
+
+            b = sharded.sharded_commit_from_values(engine, comm, work, P, n_log, RATE_BITS, CAP_HEIGHT, on_coeffs_ready=coeffs_to_host,
+                                                   host_values=host_vals_t)
             b.cap(out=cap_host)
-            # each rank returns the coefficient columns it transformed
-            ptrs = b.device_ptrs()
-            if c1 > c0:
-                p2b._check(L.p2b_memcpy_d2h(ctx.handle, host_coef.ptr, ptrs["coeffs"] + c0 * n * 8, (c1 - c0) * n * 8))
+            copy_stream.synchronize()
             b.close()
         ctx.synchronize()
 
     for _ in range(2):
         step_e2e()
+    if world > 1 and c1 > c0:  # the overlapped copy delivered this rank's coefficient columns
+        assert torch.equal(host_coef_t[: (c1 - c0) * n], work.view(-1)[: (c1 - c0) * n].cpu()), "coefficient D2H mismatch"
     barrier()
     e2e_steps = max(3, min(args.steps, 10))
     w0 = time.perf_counter()

@@ -64,14 +64,25 @@ def node_index(sub_log, sub_digests, layer, Q):
 # ---------------------------------------------------------------------------------------------------------------
 # orchestration
 # ---------------------------------------------------------------------------------------------------------------
-def sharded_commit_from_values(engine, comm, values_shard, num_polys, n_log, rate_bits, cap_height):
+def sharded_commit_from_values(engine, comm, values_shard, num_polys, n_log, rate_bits, cap_height, on_coeffs_ready=None,
+                               host_values=None):
     """values_shard: this rank's columns [c0, c1) of the value matrix, engine-native array [cmax][n] (rows beyond
     c1 - c0 are padding).  Returns the engine's batch handle; afterwards engine.cap(batch) is the full cap on every
-    rank and the batch holds this rank's leaves / digests."""
+    rank and the batch holds this rank's leaves / digests.
+    on_coeffs_ready(values_shard): called as soon as this rank's coefficient columns are final (the reference keeps the
+    coefficients host-side, fri/oracle.rs:403-407: a caller starts its device-to-host copy here, overlapped with the
+    exchange, the LDE and the tree).
+    host_values: this rank's value columns in pinned HOST memory (engine-native [cmax][n]); when given they are uploaded
+    into values_shard in column groups and each group's inverse NTT starts as soon as it has landed."""
     rank, world = comm.rank, comm.world
     c0, c1, cmax = column_shard(num_polys, world, rank)
     b0, bcount = block_shard(rate_bits, world, rank)
-    engine.ifft_columns(values_shard, c1 - c0, n_log)                 # in place
+    if host_values is not None:
+        engine.ifft_columns_from_host(host_values, values_shard, c1 - c0, n_log)   # upload in column groups, each transformed as it lands
+    else:
+        engine.ifft_columns(values_shard, c1 - c0, n_log)             # in place
+    if on_coeffs_ready is not None:
+        on_coeffs_ready(values_shard)
     coeffs_all = comm.all_gather_columns(values_shard, cmax, n_log)   # [world * cmax][n]; first num_polys rows are real
     batch = engine.commit_blocks(coeffs_all, num_polys, n_log, rate_bits, cap_height, b0, bcount)
     top = local_top_layer(n_log, rate_bits, cap_height, world)
@@ -119,6 +130,28 @@ class GpuEngine:
             return
         self._sync_in()
         self._check(self.lib.p2b_ifft_batch(self.ctx.handle, t.data_ptr(), t.data_ptr(), n_log, ncols))
+        self.ctx.synchronize()
+
+    def ifft_columns_from_host(self, host_t, t, ncols, n_log, groups=8):
+        """H2D on a copy stream in column groups; the library's stream waits for each group's event and transforms it."""
+        if ncols == 0:
+            return
+        torch = self.torch
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream()
+            self.lib.p2b_ctx_stream.restype = C.c_void_p
+            self._lib_stream = torch.cuda.ExternalStream(self.lib.p2b_ctx_stream(self.ctx.handle))
+        self._sync_in()
+        for g in range(groups):
+            a, b = ncols * g // groups, ncols * (g + 1) // groups
+            if a == b:
+                continue
+            with torch.cuda.stream(self._copy_stream):
+                t[a:b].copy_(host_t[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            self._lib_stream.wait_event(ev)
+            self._check(self.lib.p2b_ifft_batch(self.ctx.handle, t[a:b].data_ptr(), t[a:b].data_ptr(), n_log, b - a))
         self.ctx.synchronize()
 
     def commit_blocks(self, coeffs, num_polys, n_log, rate_bits, cap_height, b0, bcount):
