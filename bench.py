@@ -180,14 +180,23 @@ def run_b200(args, rank, world, local_rank):
     L = p2b.lib()
     n_log, P = args.n_log, args.polys
     n, N = 1 << n_log, 1 << (n_log + RATE_BITS)
-    c0, c1, cmax = sharded.column_shard(P, world, rank)
-
     # ---- inputs resident in HBM: this rank's columns of the synthetic value matrix ----
-    vals = torch.empty((cmax, n), dtype=torch.int64, device="cuda")
+    # N = 1: all P columns.  N > 1: the rank's 8-column blocks of the pipelined flow (sharded.cyclic_column_blocks: block q =
+    # columns [8q, 8q + 8) belongs to rank q % N), rows [8j, 8j + 8) = its block of exchange round j, zero rows where absent.
+    pipelined = world > 1 and P > 4 and not os.environ.get("P2B_BENCH_UNPIPELINED")  # env knob: A/B against the one-shot exchange
+    if pipelined:
+        rounds, my_blocks = sharded.cyclic_column_blocks(P, world, rank)
+        cmax = rounds * 8
+        col_ranges = [(8 * j, 8 * q, min(8 * q + 8, P)) for j, q in enumerate(my_blocks) if q is not None]   # (local row, c0, c1)
+    else:
+        c0, c1, cmax = sharded.column_shard(P, world, rank)
+        col_ranges = [(0, c0, c1)] if c1 > c0 else []
+    own_cols = sum(b_ - a_ for _, a_, b_ in col_ranges)
+    vals = torch.zeros((cmax, n), dtype=torch.int64, device="cuda")
     work = torch.empty_like(vals)
     torch.cuda.synchronize()
-    if c1 > c0:
-        p2b._check(L.p2b_fill_synthetic(ctx.handle, vals.data_ptr(), (c1 - c0) * n, SEED, c0 * n))
+    for row, a_, b_ in col_ranges:
+        p2b._check(L.p2b_fill_synthetic(ctx.handle, vals.data_ptr() + row * n * 8, (b_ - a_) * n, SEED, a_ * n))
     ctx.synchronize()
     engine = sharded.GpuEngine(ctx)
     comm = sharded.TorchComm(dist) if world > 1 else None
@@ -199,12 +208,14 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
+    commit_sharded = sharded.sharded_commit_from_values_pipelined if pipelined else sharded.sharded_commit_from_values
+
     def step_device():
         if world == 1:
             b = p2b.PolynomialBatch.from_values(ctx, (_Ptr(vals.data_ptr()), P, n), RATE_BITS, CAP_HEIGHT)
         else:
             work.copy_(vals)  # the sharded path transforms its columns in place
-            b = sharded.sharded_commit_from_values(engine, comm, work, P, n_log, RATE_BITS, CAP_HEIGHT)
+            b = commit_sharded(engine, comm, work, P, n_log, RATE_BITS, CAP_HEIGHT)
         ctx.synchronize()
         return b
 
@@ -271,12 +282,11 @@ def run_b200(args, rank, world, local_rank):
             def coeffs_to_host(shard):
                 # each rank returns the coefficient columns it transformed, on a side stream while the exchange, the LDE
                 # and the tree run (the single-GPU call does the same inside p2b_commit_from_values_ex)
-                if c1 > c0:
-                    with torch.cuda.stream(copy_stream):
-                        host_coef_t[: (c1 - c0) * n].copy_(shard.view(-1)[: (c1 - c0) * n], non_blocking=True)
+                with torch.cuda.stream(copy_stream):
+                    for row, a_, b_ in col_ranges:
+                        host_coef_t[row * n: (row + b_ - a_) * n].copy_(shard.view(-1)[row * n: (row + b_ - a_) * n], non_blocking=True)
 
-            b = sharded.sharded_commit_from_values(engine, comm, work, P, n_log, RATE_BITS, CAP_HEIGHT, on_coeffs_ready=coeffs_to_host,
-                                                   host_values=host_vals_t)
+            b = commit_sharded(engine, comm, work, P, n_log, RATE_BITS, CAP_HEIGHT, on_coeffs_ready=coeffs_to_host, host_values=host_vals_t)
             b.cap(out=cap_host)
             copy_stream.synchronize()
             b.close()
@@ -284,8 +294,9 @@ def run_b200(args, rank, world, local_rank):
 
     for _ in range(2):
         step_e2e()
-    if world > 1 and c1 > c0:  # the overlapped copy delivered this rank's coefficient columns
-        assert torch.equal(host_coef_t[: (c1 - c0) * n], work.view(-1)[: (c1 - c0) * n].cpu()), "coefficient D2H mismatch"
+    if world > 1:  # the overlapped copy delivered this rank's coefficient columns
+        for row, a_, b_ in col_ranges:
+            assert torch.equal(host_coef_t[row * n: (row + b_ - a_) * n], work.view(-1)[row * n: (row + b_ - a_) * n].cpu()), "coefficient D2H mismatch"
     barrier()
     e2e_steps = max(3, min(args.steps, 10))
     w0 = time.perf_counter()
@@ -307,11 +318,15 @@ def run_b200(args, rank, world, local_rank):
         clocks = sampler.summary() if sampler else {}
         # roofline of the dominant kernel (leaf hashing): algorithmic bytes of one launch = the rows of one coset block
         # read once + their digests written once (8*leaf_len per leaf in, 32 B per leaf out)
-        leaves_per_launch = n * (1 << RATE_BITS) // world // max(1, (1 << RATE_BITS) // world)  # = n
-        alg_bytes = leaves_per_launch * (P * 8 + 32)
+        # N = 1 (and the unpipelined flow): one launch per coset block, n leaves each.  Pipelined multi-GPU flow: the leaf
+        # hashing of the rank's N/world leaves is split over one absorb_columns_kernel launch per exchange round; a launch's
+        # algorithmic bytes / permutations are the per-step totals divided by the launches per step.
+        launches_per_step = max(hash_launches, 1) / max(args.steps, 1)
+        local_leaves = N // world
+        alg_bytes = local_leaves * (P * 8 + 32) / launches_per_step
         avg_hash_ms = hash_ms / max(hash_launches, 1)
         achieved_gbs = alg_bytes / (avg_hash_ms * 1e-3) / 1e9 if avg_hash_ms > 0 else 0.0
-        perms_per_launch = leaves_per_launch * (-(-P // 8))
+        perms_per_launch = local_leaves * (-(-P // 8)) / launches_per_step
         sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
         int_peak = INT_LANES_PER_CLK_PER_SM * 148 * sm_mhz * 1e6          # thread-instructions / s
         int_ach = perms_per_launch * INSTR_PER_PERM / (avg_hash_ms * 1e-3) if avg_hash_ms > 0 else 0.0
@@ -322,16 +337,18 @@ def run_b200(args, rank, world, local_rank):
             "config": {"workload": "PolynomialBatch::from_values 2^%d x %d Goldilocks, rate_bits 3, cap_height 4, Poseidon Merkle "
                                    "(%s)" % (n_log, P, "BASELINE.json configs[1]" if (n_log, P) == (20, 135)
                                              else "BASELINE.json configs[4] scale sweep: NOT the headline size the metric name quotes"),
-                       "sharding": "columns for iNTT, coset blocks / cap sub-trees for LDE+Merkle" if world > 1 else "single GPU",
+                       "sharding": ("8-column blocks dealt round-robin for the iNTT, one NCCL all-gather per round overlapped with LDE + progressive leaf "
+                                    "hashing of the previous round, coset blocks / cap sub-trees per rank") if pipelined
+                       else ("columns for iNTT, coset blocks / cap sub-trees for LDE+Merkle" if world > 1 else "single GPU"),
                        "l2": "inputs_exceed_l2 (values %.2f GB, LDE %.2f GB per step vs 126 MB L2)" % (P * n * 8 / 1e9, P * N * 8 / 1e9),
                        "timing": "CUDA events on the library stream around all steps, max over ranks; wall %.1f ms/step" % (wall_ms / args.steps),
                        "cap_word0": "%016x" % int(cap_check[0][0])},
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "steps": e2e_steps, "note": "pinned host values -> p2b_commit_from_values -> D2H coefficients + cap; host wall clock, max over ranks"},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "merkle::hash_leaves_kernel", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"],
+            "roofline": {"bound": "hbm", "kernel": "merkle::absorb_columns_kernel (leaf hashing, one launch per exchange round)" if pipelined else "merkle::hash_leaves_kernel", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"],
-                         "traffic": HASH_LAUNCH_DRAM_BYTES_2P20_X135 if (n_log == 20 and P == 135) else None, "peak_source": peak_kind + " (burst copy bandwidth)",
+                         "traffic": HASH_LAUNCH_DRAM_BYTES_2P20_X135 if (n_log == 20 and P == 135 and not pipelined) else None, "peak_source": peak_kind + " (burst copy bandwidth)",
                          "launches_timed": hash_launches, "avg_launch_ms": avg_hash_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "share_of_step": hash_ms / max(dev_ms, 1e-9)},
             "roofline_int": {"bound": "integer issue (64 INT32 lanes/clk/SM measured)", "achieved": int_ach / 1e12, "peak": int_peak / 1e12,

@@ -141,6 +141,16 @@ int p2b_batch_open_rows(const p2b_batch* b, const uint64_t* leaf_indices, uint64
 int p2b_commit_blocks(p2b_ctx* ctx, const uint64_t* d_coeffs, uint32_t n_log, uint64_t P, uint32_t rate_bits,
                       uint32_t cap_height, const uint64_t* d_salt /* device [4][N] or NULL */, uint64_t block_first,
                       uint64_t block_count, p2b_batch** out);
+/* Pipelined variant of p2b_commit_blocks for the multi-GPU flow: the coefficient columns arrive in groups (one all-gather
+ * round each); every group is low-degree-extended into the leaf rows and absorbed by the leaves' sponges at once, so the
+ * exchange of group g+1 overlaps the LDE + hashing of group g.  Groups are absorbed in column order; every group but the
+ * last holds a multiple of 8 columns (the sponge rate, hashing.rs:81-104).  After _finish the batch is identical to one
+ * produced by p2b_commit_blocks (same leaves, digests up to the local top layer).  No blinding; num_polys > 4. */
+int p2b_commit_blocks_begin(p2b_ctx* ctx, uint32_t n_log, uint64_t num_polys, uint32_t rate_bits, uint32_t cap_height,
+                            uint64_t block_first, uint64_t block_count, p2b_batch** out);
+int p2b_commit_blocks_absorb(p2b_batch* batch, const uint64_t* d_coeff_cols /* [ncols][n] */, uint64_t col0, uint64_t ncols);
+int p2b_commit_blocks_finish(p2b_batch* batch);
+
 int p2b_batch_shard_info(const p2b_batch* b, uint64_t* first_leaf, uint64_t* local_leaves, uint32_t* top_layer,
                          uint64_t* top_node_first, uint64_t* top_node_count);
 int p2b_batch_export_nodes(const p2b_batch* b, uint32_t layer, uint64_t node_first, uint64_t count,

@@ -160,6 +160,9 @@ def lib():
         "p2b_batch_prove": (i, [vp, vp, u64, vp]),
         "p2b_batch_open_rows": (i, [vp, vp, u64, vp, vp]),
         "p2b_commit_blocks": (i, [vp, vp, u32, u64, u32, u32, vp, u64, u64, C.POINTER(vp)]),
+        "p2b_commit_blocks_begin": (i, [vp, u32, u64, u32, u32, u64, u64, C.POINTER(vp)]),
+        "p2b_commit_blocks_absorb": (i, [vp, vp, u64, u64]),
+        "p2b_commit_blocks_finish": (i, [vp]),
         "p2b_batch_shard_info": (i, [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u32), C.POINTER(u64), C.POINTER(u64)]),
         "p2b_batch_export_nodes": (i, [vp, u32, u64, u64, vp]),
         "p2b_batch_import_nodes": (i, [vp, u32, u64, u64, vp]),

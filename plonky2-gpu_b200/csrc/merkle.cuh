@@ -118,6 +118,57 @@ hash_leaves_kernel(const u64* __restrict__ leaves, u64 row_stride, u64 col_strid
   if (live) store_hash(node_slot(shape, digests, cap, 0, leaf_index0 + i), h);
 }
 
+// Progressive sponge for the pipelined (multi-GPU) commit: absorbs columns [col0, col0 + ncols) of every leaf.  col0 is a
+// multiple of 8 and ncols a multiple of 8 unless this is the last call (col0 + ncols == leaf_len), so the chunking is
+// exactly the one-shot sponge's (hashing.rs:81-104).  Between calls the 12-word state of leaf i lives in
+// state[k * count + i]; the last call writes the digest.  leaf_len > 4 (hash_or_noop's copy case never gets here).
+template <class M>
+__device__ __forceinline__ void absorb_columns(const u64* __restrict__ row, u32 ncols, u64 (&s)[12], M& m) {
+  const u64* p = row;
+#pragma unroll 1
+  for (u32 left = ncols; left > 0; left = left > 8 ? left - 8 : 0) {
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      if ((u32)i < left) s[i] = __ldg(p + i);
+    p += 8;
+    poseidon::permute(s, m);
+  }
+}
+__global__ void __launch_bounds__(P2B_HASH_BLOCK, P2B_HASH_MIN_BLOCKS)
+absorb_columns_kernel(const u64* __restrict__ leaves, u64 row_stride, u32 col0, u32 ncols, int last, u64 count, u64 leaf_index0,
+                      TreeShape shape, u64* __restrict__ state, u64* __restrict__ digests, u64* __restrict__ cap) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < count;
+  if (!live) i = count - 1;
+  const u64* row = leaves + i * row_stride + col0;
+  u64 s[12];
+  auto load_state = [&]() {
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = col0 ? state[(u64)k * count + i] : 0;
+  };
+  load_state();
+#ifndef P2B_EXACT_ONLY
+  gl::Optimistic fast;
+  absorb_columns(row, ncols, s, fast);
+  if (fast.rare)  // redo this leaf's chunk exactly from the stored state (not yet overwritten)
+#endif
+  {
+    gl::Exact exact;
+    load_state();
+    absorb_columns(row, ncols, s, exact);
+  }
+  if (!live) return;
+  if (last) {
+    u64 h[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) h[k] = gl::canon(s[k]);
+    store_hash(node_slot(shape, digests, cap, 0, leaf_index0 + i), h);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 12; k++) state[(u64)k * count + i] = s[k];
+  }
+}
+
 // One thread per node of layer `l` (l >= 1): parent of nodes 2Q, 2Q+1 of layer l-1.
 __global__ void __launch_bounds__(P2B_HASH_BLOCK, P2B_HASH_MIN_BLOCKS)
 merkle_layer_kernel(TreeShape shape, u32 l, u64 node0, u64 count, u64* __restrict__ digests, u64* __restrict__ cap) {

@@ -516,6 +516,10 @@ struct p2b_batch {
   u64* digests = nullptr;
   u64* cap = nullptr;
   merkle::TreeShape shape{};
+  // pipelined commit (p2b_commit_blocks_begin / _absorb / _finish): sponge states of the local leaves, columns absorbed
+  u64* sponge_state = nullptr;
+  u64 cols_done = 0;
+  bool pipelined = false;
 };
 
 static int batch_free(p2b_batch* b) {
@@ -525,6 +529,7 @@ static int batch_free(p2b_batch* b) {
   if (b->leaves) cudaFreeAsync(b->leaves, st);
   if (b->digests) cudaFreeAsync(b->digests, st);
   if (b->cap) cudaFreeAsync(b->cap, st);
+  if (b->sponge_state) cudaFreeAsync(b->sponge_state, st);
   delete b;
   return P2B_OK;
 }
@@ -690,6 +695,114 @@ extern "C" int p2b_commit_blocks(p2b_ctx* ctx, const uint64_t* d_coeffs, uint32_
                                  p2b_batch** out) {
   return commit_impl(ctx, d_coeffs, 0, false, n_log, P, rate_bits, cap_height, d_salt, 0, out, block_first, block_count);
 }
+// ======================================================================================================
+// pipelined commit of coset blocks: coefficient columns arrive in groups (one all-gather round each in the multi-GPU
+// flow); each group is low-degree-extended into the leaf rows and absorbed by the leaves' sponges at once, so the
+// exchange of group g+1 overlaps the LDE + hashing of group g.  Same results as p2b_commit_blocks.
+// ======================================================================================================
+extern "C" int p2b_commit_blocks_begin(p2b_ctx* c, uint32_t k, uint64_t P, uint32_t rate_bits, uint32_t cap_height,
+                                       uint64_t block_first, uint64_t block_count, p2b_batch** out) {
+  if (!c || !out) return fail(P2B_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  if (P == 0) return fail(P2B_ERR_INVALID, "empty batch (no polynomials)");
+  if (P <= 4) return fail(P2B_ERR_UNSUPPORTED, "pipelined commit needs more than 4 polynomials (hash_or_noop copies shorter leaves)");
+  if (k + rate_bits > 32) return fail(P2B_ERR_INVALID, "degree_log + rate_bits = %u exceeds the field's two-adicity 32", k + rate_bits);
+  if (P > 65535) return fail(P2B_ERR_INVALID, "more than 65535 polynomials");
+  const u64 n = (u64)1 << k, N = n << rate_bits, R = (u64)1 << rate_bits;
+  const u32 log_N = k + rate_bits;
+  if (cap_height > log_N) return fail(P2B_ERR_INVALID, "cap_height=%u should be at most log2(leaves.len())=%u", cap_height, log_N);
+  if (block_first >= R || block_count == 0 || block_first + block_count > R)
+    return fail(P2B_ERR_INVALID, "coset block range [%llu, +%llu) outside 2^rate_bits = %llu", (unsigned long long)block_first,
+                (unsigned long long)block_count, (unsigned long long)R);
+  CUDA_TRY(cudaSetDevice(c->device));
+  const u64 ncap = (u64)1 << cap_height, ndig = 2 * (N - ncap);
+  p2b_batch* b = new (std::nothrow) p2b_batch();
+  if (!b) return fail(P2B_ERR_OOM, "host allocation failed");
+  b->ctx = c;
+  b->info = p2b_batch_info{k, rate_bits, cap_height, 0, P, N, P, ndig};
+  b->shape = merkle::make_shape(log_N, cap_height);
+  b->first_leaf = block_first * n;
+  b->local_leaves = block_count * n;
+  b->pipelined = true;
+  cudaStream_t st = c->stream;
+  auto body = [&]() -> int {
+    CUDA_TRY(cudaMallocAsync(&b->coeffs, P * n * sizeof(u64), st));
+    CUDA_TRY(cudaMallocAsync(&b->leaves, b->local_leaves * P * sizeof(u64), st));
+    CUDA_TRY(cudaMallocAsync(&b->digests, (ndig ? ndig : 1) * 4 * sizeof(u64), st));
+    CUDA_TRY(cudaMallocAsync(&b->cap, ncap * 4 * sizeof(u64), st));
+    CUDA_TRY(cudaMallocAsync(&b->sponge_state, 12 * b->local_leaves * sizeof(u64), st));
+    P2B_TRY(ensure_twiddles(c, log_N > 0 ? log_N - 1 : 0));
+    return P2B_OK;
+  };
+  int rc = body();
+  if (rc != P2B_OK) {
+    batch_free(b);
+    return rc;
+  }
+  *out = b;
+  return P2B_OK;
+}
+
+extern "C" int p2b_commit_blocks_absorb(p2b_batch* b, const uint64_t* d_coeff_cols, uint64_t col0, uint64_t ncols) {
+  if (!b || !d_coeff_cols) return fail(P2B_ERR_INVALID, "NULL argument");
+  if (!b->pipelined) return fail(P2B_ERR_INVALID, "batch was not created by p2b_commit_blocks_begin");
+  const u64 P = b->info.num_polys;
+  if (col0 != b->cols_done) return fail(P2B_ERR_INVALID, "columns must be absorbed in order: expected column %llu, got %llu",
+                                        (unsigned long long)b->cols_done, (unsigned long long)col0);
+  if (ncols == 0 || col0 + ncols > P) return fail(P2B_ERR_INVALID, "column range [%llu, +%llu) outside the %llu polynomials",
+                                                  (unsigned long long)col0, (unsigned long long)ncols, (unsigned long long)P);
+  const bool last = col0 + ncols == P;
+  if (!last && (ncols % 8)) return fail(P2B_ERR_INVALID, "every group but the last must hold a multiple of 8 columns (sponge rate)");
+  p2b_ctx* c = b->ctx;
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const u32 k = b->info.degree_log;
+  const u64 n = (u64)1 << k;
+  u64* dst = b->coeffs + col0 * n;
+  if (dst != d_coeff_cols) CUDA_TRY(cudaMemcpyAsync(dst, d_coeff_cols, ncols * n * sizeof(u64), cudaMemcpyDeviceToDevice, st));
+  P2B_TRY(ensure_scratch(c, ncols * n));
+  ntt::LevelScale sc = lde_scale(k);
+  const u64 block_first = b->first_leaf / n, block_count = b->local_leaves / n;
+  for (u64 i = 0; i < block_count; i++)
+    P2B_TRY(run_lde_block(c, st, dst, n, c->scratch, k, ncols, block_first + i, sc, b->leaves, P, col0, i * n));
+  const u64 count = b->local_leaves;
+  unsigned blocks = (unsigned)((count + P2B_HASH_BLOCK - 1) / P2B_HASH_BLOCK);
+  std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
+  if (c->time_hash) {
+    if (c->hash_events_used == c->hash_events.size()) {
+      cudaEvent_t a, e2;
+      CUDA_TRY(cudaEventCreate(&a));
+      CUDA_TRY(cudaEventCreate(&e2));
+      c->hash_events.emplace_back(a, e2);
+    }
+    ev = &c->hash_events[c->hash_events_used++];
+    CUDA_TRY(cudaEventRecord(ev->first, st));
+  }
+  merkle::absorb_columns_kernel<<<blocks, P2B_HASH_BLOCK, 0, st>>>(b->leaves, P, (u32)col0, (u32)ncols, last ? 1 : 0, count, b->first_leaf,
+                                                                   b->shape, b->sponge_state, b->digests, b->cap);
+  if (ev) CUDA_TRY(cudaEventRecord(ev->second, st));
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  b->cols_done = col0 + ncols;
+  return P2B_OK;
+}
+
+extern "C" int p2b_commit_blocks_finish(p2b_batch* b) {
+  if (!b) return fail(P2B_ERR_INVALID, "NULL batch");
+  if (!b->pipelined) return fail(P2B_ERR_INVALID, "batch was not created by p2b_commit_blocks_begin");
+  if (b->cols_done != b->info.num_polys)
+    return fail(P2B_ERR_INVALID, "only %llu of %llu columns absorbed", (unsigned long long)b->cols_done, (unsigned long long)b->info.num_polys);
+  p2b_ctx* c = b->ctx;
+  CUDA_TRY(cudaSetDevice(c->device));
+  P2B_TRY(launch_layers(c, c->stream, b->shape, b->digests, b->cap, b->first_leaf, b->first_leaf + b->local_leaves, 0, &b->top_layer));
+  if (b->sponge_state) {
+    cudaFreeAsync(b->sponge_state, c->stream);
+    b->sponge_state = nullptr;
+  }
+  b->pipelined = false;
+  return P2B_OK;
+}
+
 extern "C" int p2b_batch_shard_info(const p2b_batch* b, uint64_t* first_leaf, uint64_t* local_leaves, uint32_t* top_layer,
                                     uint64_t* top_node_first, uint64_t* top_node_count) {
   if (!b) return fail(P2B_ERR_INVALID, "NULL batch");

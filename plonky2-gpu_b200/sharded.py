@@ -94,6 +94,57 @@ def sharded_commit_from_values(engine, comm, values_shard, num_polys, n_log, rat
     return batch
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# pipelined variant: the exchange of one column group overlaps the LDE + leaf hashing of the previous one
+# ---------------------------------------------------------------------------------------------------------------
+SPONGE_RATE = 8
+
+
+def cyclic_column_blocks(num_polys, world, rank):
+    """Column blocks of SPONGE_RATE columns dealt round-robin: block q = columns [8q, 8q + 8) belongs to rank q % world and
+    is exchanged in round q // world, so that one all-gather round delivers 8 * world CONSECUTIVE columns -- the order in
+    which the leaves' sponges absorb them (hashing.rs:81-104).  Returns (rounds, [block index or None per round])."""
+    nblocks = -(-num_polys // SPONGE_RATE)
+    rounds = -(-nblocks // world)
+    mine = [j * world + rank if j * world + rank < nblocks else None for j in range(rounds)]
+    return rounds, mine
+
+
+def sharded_commit_from_values_pipelined(engine, comm, values_blocks, num_polys, n_log, rate_bits, cap_height,
+                                         on_coeffs_ready=None, host_values=None):
+    """Same result as sharded_commit_from_values with the exchange hidden behind the hashing.
+    values_blocks: this rank's column blocks, engine-native [rounds * 8][n]: rows [8j, 8j + 8) = block
+    cyclic_column_blocks(...)[1][j] (zero rows where the block is short or absent).  Steps: inverse NTT of the local
+    blocks; one asynchronous all-gather per round (NCCL runs them back to back on its own stream); as soon as round j has
+    landed its 8 * world consecutive coefficient columns are LDE'd into the leaf rows of this rank's coset blocks and
+    absorbed by the leaves' sponges (p2b_commit_blocks_absorb) while round j + 1 is still in flight; digest layers and
+    the top-layer node exchange as in the unpipelined flow."""
+    rank, world = comm.rank, comm.world
+    rounds, mine = cyclic_column_blocks(num_polys, world, rank)
+    b0, bcount = block_shard(rate_bits, world, rank)
+    ncols_local = rounds * SPONGE_RATE
+    if host_values is not None:
+        engine.ifft_columns_from_host(host_values, values_blocks, ncols_local, n_log)
+    else:
+        engine.ifft_columns(values_blocks, ncols_local, n_log)          # zero rows stay zero
+    if on_coeffs_ready is not None:
+        on_coeffs_ready(values_blocks)
+    pending = [comm.all_gather_async(values_blocks[j * SPONGE_RATE:(j + 1) * SPONGE_RATE]) for j in range(rounds)]
+    batch = engine.commit_begin(num_polys, n_log, rate_bits, cap_height, b0, bcount)
+    for j, handle in enumerate(pending):
+        cols = comm.wait(handle)                                        # [world * 8][n] = columns [64j, 64j + 64) in order
+        col0 = j * world * SPONGE_RATE
+        engine.commit_absorb(batch, cols, col0, min(world * SPONGE_RATE, num_polys - col0))
+    batch = engine.commit_finish(batch)
+    top = local_top_layer(n_log, rate_bits, cap_height, world)
+    count = ((1 << (n_log + rate_bits)) // world) >> top
+    mine_nodes = engine.export_nodes(batch, top, rank * count, count)
+    everyone = comm.all_gather_nodes(mine_nodes, count)
+    engine.import_nodes(batch, top, 0, world * count, everyone)
+    engine.finish_layers(batch, top)
+    return batch
+
+
 def sharded_open_rows(engine, comm, batch, indices, n_log, rate_bits, cap_height, leaf_len):
     """FRI query openings over a sharded batch (fri/prover.rs:187-216: `t.get(x_index)`, `t.prove(x_index)` for every
     query): the rank that owns leaf x (contiguous range [rank*N/G, (rank+1)*N/G)) gathers the row and its Merkle path --
@@ -161,6 +212,24 @@ class GpuEngine:
                                                None, b0, bcount, C.byref(h)))
         return self._PB(self.ctx, h.value)
 
+    def commit_begin(self, num_polys, n_log, rate_bits, cap_height, b0, bcount):
+        h = C.c_void_p()
+        self._check(self.lib.p2b_commit_blocks_begin(self.ctx.handle, n_log, num_polys, rate_bits, cap_height, b0, bcount, C.byref(h)))
+        self._keep = []
+        return h
+
+    def commit_absorb(self, h, cols, col0, ncols):
+        self._sync_in()          # the all-gather that produced `cols` has completed (host wait; the previous group's kernels keep running)
+        self._keep.append(cols)  # the library reads `cols` asynchronously on its stream
+        self._check(self.lib.p2b_commit_blocks_absorb(h, cols.data_ptr(), col0, ncols))
+
+    def commit_finish(self, h):
+        self._check(self.lib.p2b_commit_blocks_finish(h))
+        b = self._PB(self.ctx, h.value)
+        self.ctx.synchronize()
+        self._keep = []
+        return b
+
     def export_nodes(self, batch, layer, first, count):
         out = self.torch.empty((count, 4), dtype=self.torch.int64, device="cuda")
         self._check(self.lib.p2b_batch_export_nodes(batch.handle, layer, first, count, out.data_ptr()))
@@ -212,6 +281,20 @@ class TorchComm:
 
     def all_gather_nodes(self, t, count):
         return self._gather(t)
+
+    def all_gather_async(self, t):
+        """Starts the all-gather of `t` (same shape on every rank); returns a handle for wait()."""
+        if self.world == 1:
+            return (t, None)
+        out = self.torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        work = self.dist.all_gather_into_tensor(out, t.contiguous(), async_op=True)
+        return (out, work)
+
+    def wait(self, handle):
+        out, work = handle
+        if work is not None:
+            work.wait()
+        return out
 
     def all_reduce_sum(self, t):
         if self.world > 1:

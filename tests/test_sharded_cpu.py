@@ -113,6 +113,20 @@ class OracleEngine:
     def cap(self, b):
         return b["cap"]
 
+    def commit_begin(self, num_polys, n_log, rate_bits, cap_height, b0, bcount):
+        return {"args": (num_polys, n_log, rate_bits, cap_height, b0, bcount), "cols": [], "done": 0}
+
+    def commit_absorb(self, h, cols, col0, ncols):
+        assert col0 == h["done"] and (ncols % 8 == 0 or col0 + ncols == h["args"][0])   # the C ABI's contract
+        h["cols"].append(cols.numpy().view(np.uint64)[:ncols].copy())
+        h["done"] += ncols
+
+    def commit_finish(self, h):
+        num_polys, n_log, rate_bits, cap_height, b0, bcount = h["args"]
+        assert h["done"] == num_polys
+        co = np.concatenate(h["cols"])
+        return self.commit_blocks(torch.from_numpy(co.view(np.int64)), num_polys, n_log, rate_bits, cap_height, b0, bcount)
+
     def pack_open_rows(self, b, idx, slots, Q, leaf_len, layers):
         packed = np.zeros((Q, leaf_len + 4 * layers), dtype=np.uint64)
         for x, slot in zip(idx, slots):
@@ -125,6 +139,16 @@ class OracleEngine:
 
     def to_numpy(self, t):
         return t.numpy().view(np.uint64)
+
+
+def test_cyclic_column_blocks():
+    # 135 columns = 17 blocks of 8 on 8 ranks: 3 rounds, rank 0 holds blocks 0, 8, 16, rank 1 blocks 1, 9 and nothing in round 2
+    assert sharded.cyclic_column_blocks(135, 8, 0) == (3, [0, 8, 16])
+    assert sharded.cyclic_column_blocks(135, 8, 1) == (3, [1, 9, None])
+    assert sharded.cyclic_column_blocks(135, 2, 1) == (9, [1, 3, 5, 7, 9, 11, 13, 15, None])
+    assert sharded.cyclic_column_blocks(5, 4, 0) == (1, [0])
+    seen = sorted(q for r in range(4) for q in sharded.cyclic_column_blocks(135, 4, r)[1] if q is not None)
+    assert seen == list(range(17))
 
 
 def _free_port():
@@ -160,6 +184,18 @@ def _worker(rank, world, port, n_log, P, rate_bits, cap_height, q):
         for x, r, sb in zip(idx, rows, sibs):
             ok = ok and np.array_equal(r, ref.leaves[x]) and oracle.merkle_verify(r, x, ref.cap, sb)
             ok = ok and np.array_equal(sb, oracle.merkle_prove(ref.digests, N, cap_height, x))
+        # pipelined variant (cyclic 8-column blocks, one all-gather round per group): same cap, coefficients, leaves
+        rounds, mine = sharded.cyclic_column_blocks(P, world, rank)
+        blocks = np.zeros((rounds * 8, 1 << n_log), dtype=np.uint64)
+        for j, qb in enumerate(mine):
+            if qb is not None:
+                cols = values[8 * qb: min(8 * qb + 8, P)]
+                blocks[8 * j: 8 * j + cols.shape[0]] = cols
+        if P > 4:
+            pb = sharded.sharded_commit_from_values_pipelined(OracleEngine(), comm, torch.from_numpy(blocks.view(np.int64)), P, n_log,
+                                                              rate_bits, cap_height)
+            ok = ok and np.array_equal(pb["cap"], ref.cap) and np.array_equal(pb["coeffs"], ref.coeffs)
+            ok = ok and np.array_equal(pb["leaves"], ref.leaves[b0 * n:(b0 + bc) * n])
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
