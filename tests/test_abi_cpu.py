@@ -62,3 +62,17 @@ def test_product_never_touches_the_oracle():
                     if re.search(r"p2oracle|import oracle|from oracle|oracle/", txt):
                         bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_header_is_plain_c99():
+    """The drop-in boundary is a C ABI: the header must compile as C (no C++-isms, no torch / CUDA types in signatures)."""
+    import subprocess
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "h.c")
+        open(src, "w").write('#include "include/plonky2_b200.h"\nint main(void) { p2b_challenger c; (void)c; return 0; }\n')
+        r = subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I" + ROOT, src],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    text = open(os.path.join(ROOT, "include", "plonky2_b200.h")).read()
+    assert "torch" not in text and "cuda_runtime" not in text and "cudaStream_t" not in text.split("*/")[-1]
