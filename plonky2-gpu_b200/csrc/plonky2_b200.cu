@@ -573,6 +573,8 @@ static int lde_and_merkle(p2b_ctx* c, const u64* coeffs_d, u32 k, u64 P, u32 rat
   return P2B_OK;
 }
 
+static int lde_and_absorb_group(p2b_batch* b, u64 col0, u64 ncols, bool hash_on_stream2);
+
 static int commit_impl(p2b_ctx* c, const u64* input, int on_host, bool is_values, u32 k, u64 P, u32 rate_bits,
                        u32 cap_height, const u64* salt, int salt_on_host, p2b_batch** out, u64 block_first = 0,
                        u64 block_count = ~(u64)0, u64* coeffs_host_out = nullptr) {
@@ -613,6 +615,42 @@ static int commit_impl(p2b_ctx* c, const u64* input, int on_host, bool is_values
     P2B_TRY(ensure_scratch(c, P * n));
     const u64* in_d = input;
     bool ifft_done = false;
+    if (on_host && is_values && !salt && P >= 16 && block_first == 0 && block_count == R) {
+      // Host values, whole batch: everything is pipelined behind the upload.  Groups of 16 columns (two sponge blocks):
+      // H2D on the copy stream -> inverse NTT -> (coefficients back to the host on the other DMA engine) -> LDE into the
+      // leaf rows -> the leaves' sponges absorb the group on stream2 while the next group uploads and transforms.
+      // Only the first group's upload is exposed (the one-shot flow waits for the whole matrix before it can hash).
+      const u64 gcols = 16;
+      const u64 ngroups = (P + gcols - 1) / gcols;
+      CUDA_TRY(cudaMallocAsync(&b->sponge_state, 12 * b->local_leaves * sizeof(u64), st));
+      P2B_TRY(ensure_twiddles(c, log_N > 0 ? log_N - 1 : 0));
+      CUDA_TRY(cudaEventRecord(c->ev_copy[31], st));                 // allocations above are stream-ordered on st
+      CUDA_TRY(cudaStreamWaitEvent(c->stream_h2d, c->ev_copy[31], 0));
+      for (u64 g = 0; g < ngroups; g++) {
+        const u64 c0 = g * gcols, c1 = std::min<u64>(P, c0 + gcols);
+        cudaEvent_t ev_up = c->ev_copy[g % 14], ev_dn = c->ev_copy[14 + g % 14];
+        CUDA_TRY(cudaMemcpyAsync(b->coeffs + c0 * n, input + c0 * n, (c1 - c0) * n * sizeof(u64), cudaMemcpyHostToDevice, c->stream_h2d));
+        CUDA_TRY(cudaEventRecord(ev_up, c->stream_h2d));
+        CUDA_TRY(cudaStreamWaitEvent(st, ev_up, 0));
+        P2B_TRY(run_ifft(c, b->coeffs + c0 * n, b->coeffs + c0 * n, c->scratch + c0 * n, k, c1 - c0));
+        if (coeffs_host_out) {
+          CUDA_TRY(cudaEventRecord(ev_dn, st));
+          CUDA_TRY(cudaStreamWaitEvent(c->stream_d2h, ev_dn, 0));
+          CUDA_TRY(cudaMemcpyAsync(coeffs_host_out + c0 * n, b->coeffs + c0 * n, (c1 - c0) * n * sizeof(u64), cudaMemcpyDeviceToHost, c->stream_d2h));
+        }
+        P2B_TRY(lde_and_absorb_group(b, c0, c1 - c0, true));
+      }
+      CUDA_TRY(cudaEventRecord(c->ev_b, c->stream2));
+      CUDA_TRY(cudaStreamWaitEvent(st, c->ev_b, 0));
+      P2B_TRY(launch_layers(c, st, b->shape, b->digests, b->cap, b->first_leaf, b->first_leaf + b->local_leaves, 0, &b->top_layer));
+      if (coeffs_host_out) {
+        CUDA_TRY(cudaEventRecord(c->ev_copy[29], c->stream_d2h));
+        CUDA_TRY(cudaStreamWaitEvent(st, c->ev_copy[29], 0));      // a later synchronisation of the main stream covers the copies
+      }
+      CUDA_TRY(cudaFreeAsync(b->sponge_state, st));
+      b->sponge_state = nullptr;
+      return P2B_OK;
+    }
     if (on_host && is_values && P >= 16) {
       // Host values: H2D in column groups on the copy stream, each group's inverse NTT starts as soon as its columns
       // have landed (the transform is per column), so only the last group's transform is exposed after the copy.
@@ -743,6 +781,49 @@ extern "C" int p2b_commit_blocks_begin(p2b_ctx* c, uint32_t k, uint64_t P, uint3
   return P2B_OK;
 }
 
+// LDE of coefficient columns [col0, col0 + ncols) (already in b->coeffs) into the leaf rows of the batch's coset blocks on
+// the main stream, then the leaves' sponges absorb them -- on stream2 when `hash_on_stream2` (the caller's next group then
+// transforms on the main stream meanwhile; absorbs stay ordered among themselves on stream2).
+static int lde_and_absorb_group(p2b_batch* b, u64 col0, u64 ncols, bool hash_on_stream2) {
+  p2b_ctx* c = b->ctx;
+  cudaStream_t st = c->stream;
+  const u64 P = b->info.num_polys;
+  const u32 k = b->info.degree_log;
+  const u64 n = (u64)1 << k;
+  const bool last = col0 + ncols == P;
+  P2B_TRY(ensure_scratch(c, ncols * n));
+  ntt::LevelScale sc = lde_scale(k);
+  const u64 block_first = b->first_leaf / n, block_count = b->local_leaves / n;
+  for (u64 i = 0; i < block_count; i++)
+    P2B_TRY(run_lde_block(c, st, b->coeffs + col0 * n, n, c->scratch, k, ncols, block_first + i, sc, b->leaves, P, col0, i * n));
+  cudaStream_t hs = st;
+  if (hash_on_stream2) {
+    CUDA_TRY(cudaEventRecord(c->ev_a, st));
+    CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->ev_a, 0));
+    hs = c->stream2;
+  }
+  const u64 count = b->local_leaves;
+  unsigned blocks = (unsigned)((count + P2B_HASH_BLOCK - 1) / P2B_HASH_BLOCK);
+  std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
+  if (c->time_hash) {
+    if (c->hash_events_used == c->hash_events.size()) {
+      cudaEvent_t a, e2;
+      CUDA_TRY(cudaEventCreate(&a));
+      CUDA_TRY(cudaEventCreate(&e2));
+      c->hash_events.emplace_back(a, e2);
+    }
+    ev = &c->hash_events[c->hash_events_used++];
+    CUDA_TRY(cudaEventRecord(ev->first, hs));
+  }
+  merkle::absorb_columns_kernel<<<blocks, P2B_HASH_BLOCK, 0, hs>>>(b->leaves, P, (u32)col0, (u32)ncols, last ? 1 : 0, count, b->first_leaf,
+                                                                   b->shape, b->sponge_state, b->digests, b->cap);
+  if (ev) CUDA_TRY(cudaEventRecord(ev->second, hs));
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  b->cols_done = col0 + ncols;
+  return P2B_OK;
+}
+
 extern "C" int p2b_commit_blocks_absorb(p2b_batch* b, const uint64_t* d_coeff_cols, uint64_t col0, uint64_t ncols) {
   if (!b || !d_coeff_cols) return fail(P2B_ERR_INVALID, "NULL argument");
   if (!b->pipelined) return fail(P2B_ERR_INVALID, "batch was not created by p2b_commit_blocks_begin");
@@ -755,36 +836,10 @@ extern "C" int p2b_commit_blocks_absorb(p2b_batch* b, const uint64_t* d_coeff_co
   if (!last && (ncols % 8)) return fail(P2B_ERR_INVALID, "every group but the last must hold a multiple of 8 columns (sponge rate)");
   p2b_ctx* c = b->ctx;
   CUDA_TRY(cudaSetDevice(c->device));
-  cudaStream_t st = c->stream;
-  const u32 k = b->info.degree_log;
-  const u64 n = (u64)1 << k;
+  const u64 n = (u64)1 << b->info.degree_log;
   u64* dst = b->coeffs + col0 * n;
-  if (dst != d_coeff_cols) CUDA_TRY(cudaMemcpyAsync(dst, d_coeff_cols, ncols * n * sizeof(u64), cudaMemcpyDeviceToDevice, st));
-  P2B_TRY(ensure_scratch(c, ncols * n));
-  ntt::LevelScale sc = lde_scale(k);
-  const u64 block_first = b->first_leaf / n, block_count = b->local_leaves / n;
-  for (u64 i = 0; i < block_count; i++)
-    P2B_TRY(run_lde_block(c, st, dst, n, c->scratch, k, ncols, block_first + i, sc, b->leaves, P, col0, i * n));
-  const u64 count = b->local_leaves;
-  unsigned blocks = (unsigned)((count + P2B_HASH_BLOCK - 1) / P2B_HASH_BLOCK);
-  std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
-  if (c->time_hash) {
-    if (c->hash_events_used == c->hash_events.size()) {
-      cudaEvent_t a, e2;
-      CUDA_TRY(cudaEventCreate(&a));
-      CUDA_TRY(cudaEventCreate(&e2));
-      c->hash_events.emplace_back(a, e2);
-    }
-    ev = &c->hash_events[c->hash_events_used++];
-    CUDA_TRY(cudaEventRecord(ev->first, st));
-  }
-  merkle::absorb_columns_kernel<<<blocks, P2B_HASH_BLOCK, 0, st>>>(b->leaves, P, (u32)col0, (u32)ncols, last ? 1 : 0, count, b->first_leaf,
-                                                                   b->shape, b->sponge_state, b->digests, b->cap);
-  if (ev) CUDA_TRY(cudaEventRecord(ev->second, st));
-  c->launches++;
-  CUDA_TRY(cudaGetLastError());
-  b->cols_done = col0 + ncols;
-  return P2B_OK;
+  if (dst != d_coeff_cols) CUDA_TRY(cudaMemcpyAsync(dst, d_coeff_cols, ncols * n * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream));
+  return lde_and_absorb_group(b, col0, ncols, false);
 }
 
 extern "C" int p2b_commit_blocks_finish(p2b_batch* b) {
