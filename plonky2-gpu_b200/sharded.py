@@ -122,19 +122,28 @@ def sharded_commit_from_values_pipelined(engine, comm, values_blocks, num_polys,
     rank, world = comm.rank, comm.world
     rounds, mine = cyclic_column_blocks(num_polys, world, rank)
     b0, bcount = block_shard(rate_bits, world, rank)
-    ncols_local = rounds * SPONGE_RATE
-    if host_values is not None:
-        engine.ifft_columns_from_host(host_values, values_blocks, ncols_local, n_log)
-    else:
-        engine.ifft_columns(values_blocks, ncols_local, n_log)          # zero rows stay zero
-    if on_coeffs_ready is not None:
-        on_coeffs_ready(values_blocks)
-    pending = [comm.all_gather_async(values_blocks[j * SPONGE_RATE:(j + 1) * SPONGE_RATE]) for j in range(rounds)]
     batch = engine.commit_begin(num_polys, n_log, rate_bits, cap_height, b0, bcount)
-    for j, handle in enumerate(pending):
-        cols = comm.wait(handle)                                        # [world * 8][n] = columns [64j, 64j + 64) in order
+    pending = []
+
+    def absorb(j):
+        cols = comm.wait(pending[j])                                    # [world * 8][n] = columns [8 world j, 8 world (j+1)) in order
         col0 = j * world * SPONGE_RATE
         engine.commit_absorb(batch, cols, col0, min(world * SPONGE_RATE, num_polys - col0))
+
+    # software pipeline over the rounds: (upload +) inverse NTT of block j -> its all-gather starts -> LDE + absorb of
+    # round j - 1 is enqueued, so the GPU hashes round j - 1 while round j is exchanged and block j + 1 is uploaded
+    if host_values is None:
+        engine.ifft_columns(values_blocks, rounds * SPONGE_RATE, n_log)  # device-resident input: all local blocks at once (zero rows stay zero)
+    for j in range(rounds):
+        blk = values_blocks[j * SPONGE_RATE:(j + 1) * SPONGE_RATE]
+        if host_values is not None:
+            engine.ifft_columns_from_host(host_values[j * SPONGE_RATE:(j + 1) * SPONGE_RATE], blk, SPONGE_RATE, n_log, groups=1)
+        pending.append(comm.all_gather_async(blk))
+        if j >= 1:
+            absorb(j - 1)
+    if on_coeffs_ready is not None:
+        on_coeffs_ready(values_blocks)
+    absorb(rounds - 1)
     batch = engine.commit_finish(batch)
     top = local_top_layer(n_log, rate_bits, cap_height, world)
     count = ((1 << (n_log + rate_bits)) // world) >> top
