@@ -18,7 +18,7 @@ _u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("p2oracle.c", "p2oracle_quotient.c", "p2oracle.h", "poseidon_tables.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("p2oracle.c", "p2oracle.h", "poseidon_tables.h")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "libp2oracle.so"])
     return _SO

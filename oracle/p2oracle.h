@@ -3,7 +3,8 @@
  *
  * A plain-C, CPU restatement of the reference's (sideprotocol/plonky2-gpu) CPU algorithm for the
  * polynomial-commitment hot path: Goldilocks field, FFT/iFFT, coset LDE, bit-reversal, Poseidon sponge,
- * MerkleTree::new, PolynomialBatch::from_values/from_coeffs and compute_quotient_polys.
+ * MerkleTree::new and PolynomialBatch::from_values/from_coeffs (compute_quotient_polys, the permutation argument and the
+ * FRI opening proof are restated in Python: oracle/quotient.py, oracle/recursion_gates.py, oracle/fri.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may load this
  * library.  The product (plonky2-gpu_b200/) never links, imports or calls it.
