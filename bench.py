@@ -9,12 +9,13 @@
 Workload (BASELINE.json configs[1]): 2^20 rows x 135 Goldilocks columns, rate_bits = 3, cap_height = 4, Poseidon
 Merkle tree, no blinding; synthetic values from splitmix64.  A step is one commit of that matrix:
 batched inverse NTT -> coset LDE in leaf order -> leaf hashing -> digest layers -> cap.  At N > 1 the SAME commit is
-sharded over the ranks (strong scaling): columns for the iNTT, an NCCL all-gather of the coefficients, coset blocks /
-cap sub-trees for LDE + hashing, an all-gather of the cap entries.
+sharded over the ranks (strong scaling): 8-column blocks dealt round-robin for the iNTT, one NCCL all-gather of the
+coefficients per round overlapped with the LDE + progressive leaf hashing of the previous round, coset blocks / cap
+sub-trees per rank for LDE + hashing, an all-gather of the cap entries (plonky2-gpu_b200/sharded.py).
 
 Prints ONE JSON line (rank 0).  `value` = ms per commit with inputs resident in HBM (device events, max over ranks);
 `e2e` = the same through the public API from pinned HOST buffers (H2D values, D2H coefficients + cap inside the timed
-region); `roofline` = the dominant kernel (leaf hashing) against measured HBM bandwidth, with `roofline_int` giving the
+region, pipelined behind the compute in 16-column groups); `roofline` = the dominant kernel (leaf hashing) against measured HBM bandwidth, with `roofline_int` giving the
 figure that actually binds it (integer issue rate); `cpu_baseline` = the oracle port on the host cores.
 """
 import argparse
