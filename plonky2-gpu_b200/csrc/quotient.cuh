@@ -632,7 +632,7 @@ __device__ __forceinline__ void eval_batch(const Params& p, const u64 first, con
 }
 
 #ifndef P2B_QUOT_BLOCK
-#define P2B_QUOT_BLOCK 512
+#define P2B_QUOT_BLOCK 384
 #endif
 template <int NC, int PPT>
 __global__ void __launch_bounds__(P2B_QUOT_BLOCK) quotient_values_kernel(Params p) {
