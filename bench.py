@@ -52,7 +52,10 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-log", type=int, default=20, help="log2 rows (development override; the judged run uses 20)")
     ap.add_argument("--polys", type=int, default=135)
-    ap.add_argument("--cpu-sample-log", type=int, default=14, help="log2 rows of the bounded CPU sample")
+    ap.add_argument("--cpu-sample-log", type=int, default=0,
+                    help="log2 rows of the bounded CPU sample (0 = largest power of two whose run fits --cpu-budget-s)")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall-clock budget of all CPU-arm steps together")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's own CUDA kernels (oracle/_ref)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -116,10 +119,32 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port of the reference's CPU path, on all host threads
 # ---------------------------------------------------------------------------------------------------------------
+def cpu_threads():
+    """All host threads, set explicitly: torchrun exports OMP_NUM_THREADS=1, which would silently make this a 1-core run."""
+    import oracle
+    oracle.build()
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    oracle.set_threads(n)
+    return oracle.get_threads()
+
+
+def pick_cpu_sample_log(args, total_reps):
+    """Largest sample (<= the workload itself) whose `total_reps` repetitions fit the CPU budget, from a 2^13-row probe."""
+    if args.cpu_sample_log:
+        return min(args.cpu_sample_log, args.n_log)
+    probe = min(13, args.n_log)
+    ms, _ = cpu_commit_ms(probe, args.polys)
+    ms, _ = cpu_commit_ms(probe, args.polys)
+    k = probe
+    while k < args.n_log and (ms * (1 << (k + 1 - probe)) * 1.1e-3) * total_reps <= args.cpu_budget_s:
+        k += 1
+    return k
+
+
 def cpu_commit_ms(sample_log, polys, reps=1):
     """Times PolynomialBatch::from_values of the oracle on a 2^sample_log x polys sample of the workload."""
     import oracle
-    oracle.build()
+    cpu_threads()
     rng = np.random.default_rng(SEED & 0xFFFFFFFF)
     values = rng.integers(0, oracle.ORDER, size=(polys, 1 << sample_log), dtype=np.uint64)
     best = None
@@ -131,31 +156,41 @@ def cpu_commit_ms(sample_log, polys, reps=1):
     return best, oracle.get_threads()
 
 
-def cpu_baseline_obj(args, value_ms, cores, kind="port"):
-    scale = 1 << (args.n_log - args.cpu_sample_log)
-    return {"value": value_ms, "unit": "ms", "cores": cores, "kind": kind,
-            "sample": "oracle (C/OpenMP restatement of the reference CPU path) commit of 2^%d x %d, rate 3, cap 4, measured "
-                      "then scaled x%d to 2^%d rows (work is linear in rows up to the log factor of the NTT, which is <10%% of "
-                      "the time)" % (args.cpu_sample_log, args.polys, scale, args.n_log)}
+def workload_name(n_log, polys):
+    return ("PolynomialBatch::from_values 2^%d x %d Goldilocks, rate_bits 3, cap_height 4, Poseidon Merkle (%s)"
+            % (n_log, polys, "BASELINE.json configs[1]" if (n_log, polys) == (20, 135)
+               else "BASELINE.json configs[4] scale sweep: NOT the headline size the metric name quotes"))
+
+
+def cpu_baseline_obj(args, value_ms, cores, sample_log, kind="port"):
+    scale = 1 << (args.n_log - sample_log)
+    if scale == 1:
+        how = "the whole workload, measured (no scaling)"
+    else:
+        how = ("commit of 2^%d x %d measured, then scaled x%d to 2^%d rows (work is linear in rows up to the log factor of the "
+               "NTT, which is <10%% of the time)" % (sample_log, args.polys, scale, args.n_log))
+    return {"value": value_ms, "unit": "ms", "cores": cores, "kind": kind, "sample_rows_log2": sample_log,
+            "sample": "oracle (C/OpenMP restatement of the reference CPU path, all %d host threads): %s" % (cores, how)}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    scale = 1 << (args.n_log - args.cpu_sample_log)
+    sample_log = pick_cpu_sample_log(args, args.steps + args.warmup)
+    scale = 1 << (args.n_log - sample_log)
     for _ in range(args.warmup):
-        cpu_commit_ms(args.cpu_sample_log, args.polys)
+        cpu_commit_ms(sample_log, args.polys)
     times, cores = [], 1
     for _ in range(args.steps):
-        ms, cores = cpu_commit_ms(args.cpu_sample_log, args.polys)
+        ms, cores = cpu_commit_ms(sample_log, args.polys)
         times.append(ms * scale)
     ms = sum(times) / len(times)
     line = {"impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "PolynomialBatch::from_values 2^%d x %d Goldilocks, rate_bits 3, cap_height 4, Poseidon Merkle"
-                                   % (args.n_log, args.polys), "timing": "host wall clock of the CPU sample, scaled"},
-            "cpu_baseline": cpu_baseline_obj(args, ms, cores),
+            "config": {"workload": workload_name(args.n_log, args.polys),
+                       "timing": "host wall clock of the CPU run (2^%d-row sample x%d)" % (sample_log, scale)},
+            "cpu_baseline": cpu_baseline_obj(args, ms, cores, sample_log),
             "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -164,6 +199,71 @@ def run_reference(args, rank):
 # ---------------------------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------------------------
+def headline_golden_cap(n_log, polys):
+    if (n_log, polys) != (20, 135):
+        return None
+    try:
+        g = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_golden.json")))
+        return np.array(g["headline"]["cap"], dtype=np.uint64)
+    except Exception:
+        return None
+
+
+def parity_preflight(p2b, sharded, ctx, engine, comm, commit_sharded, rank, world, P, pipelined, n_log=12):
+    """Before any timing: commit a 2^12 x P slice of the synthetic matrix through the code path about to be timed and compare
+    with the CPU oracle -- at N = 1 coefficients, leaves, digests and cap; at N > 1 this rank's leaf rows, its opened rows
+    + Merkle paths (verified against the oracle's cap) and the cap.  Raises on any mismatch."""
+    import torch
+    import oracle
+    oracle.build()
+    n = 1 << n_log
+    N = n << RATE_BITS
+    L = p2b.lib()
+    full = p2b.DeviceBuffer(ctx, P * n)
+    ctx.fill_synthetic(full, P * n, SEED)
+    ctx.synchronize()
+    values = full.to_host(P * n).reshape(P, n)
+    want = oracle.batch_from_values(values, RATE_BITS, CAP_HEIGHT)
+    if world == 1:
+        b = p2b.PolynomialBatch.from_values(ctx, values, RATE_BITS, CAP_HEIGHT)
+        ok = (np.array_equal(b.cap(), want.cap) and np.array_equal(b.polynomials(), want.coeffs)
+              and np.array_equal(b.leaves(), want.leaves) and np.array_equal(b.digests(), want.digests))
+        b.close()
+        full.free()
+        if not ok:
+            raise SystemExit("bench.py: parity preflight failed (2^%d x %d commit differs from the CPU oracle)" % (n_log, P))
+        return "2^%d x %d: coefficients, leaves, digests, cap == CPU oracle" % (n_log, P)
+    if pipelined:
+        rounds, my_blocks = sharded.cyclic_column_blocks(P, world, rank)
+        shard = np.zeros((rounds * 8, n), dtype=np.uint64)
+        for j, q in enumerate(my_blocks):
+            if q is not None:
+                c0, c1 = 8 * q, min(8 * q + 8, P)
+                shard[8 * j: 8 * j + (c1 - c0)] = values[c0:c1]
+    else:
+        c0, c1, cmax = sharded.column_shard(P, world, rank)
+        shard = np.zeros((cmax, n), dtype=np.uint64)
+        shard[: c1 - c0] = values[c0:c1]
+    t = torch.from_numpy(shard.view(np.int64)).cuda()
+    b = commit_sharded(engine, comm, t, P, n_log, RATE_BITS, CAP_HEIGHT)
+    ctx.synchronize()
+    per = N // world
+    ok = np.array_equal(b.cap(), want.cap)
+    mine = b.leaves()
+    ok = ok and np.array_equal(np.asarray(mine).reshape(-1, P)[:per], want.leaves[rank * per:(rank + 1) * per])
+    idx = [int(x) for x in np.random.default_rng(5).integers(0, N, size=16)]
+    rows, sibs = sharded.sharded_open_rows(engine, comm, b, idx, n_log, RATE_BITS, CAP_HEIGHT, P)
+    for k, x in enumerate(idx):
+        ok = ok and np.array_equal(rows[k], want.leaves[x]) and oracle.merkle_verify(rows[k], x, want.cap, sibs[k])
+    b.close()
+    full.free()
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    torch.distributed.all_reduce(flag)
+    if int(flag[0]) != 0:
+        raise SystemExit("bench.py: rank %d: parity preflight failed (sharded 2^%d x %d commit differs from the CPU oracle)" % (rank, n_log, P))
+    return "2^%d x %d sharded over %d ranks: each rank's leaf rows, 16 opened rows + Merkle paths, cap == CPU oracle" % (n_log, P, world)
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import plonky2_gpu_b200 as p2b
@@ -224,6 +324,9 @@ def run_b200(args, rank, world, local_rank):
         def __init__(self, ptr):
             self.ptr = ptr
 
+    # ---- parity preflight (never timed): the same code path on a 2^12-row slice against the CPU oracle ----
+    preflight = parity_preflight(p2b, sharded, ctx, engine, comm, commit_sharded, rank, world, P, pipelined)
+
     # ---- warm-up ----
     cap_check = None
     for _ in range(max(args.warmup, 3)):
@@ -231,6 +334,15 @@ def run_b200(args, rank, world, local_rank):
         cap_check = b.cap()
         b.close()
     barrier()
+    # the full cap of the headline matrix as computed by the CPU oracle (tests/golden/oracle_golden.json, generated by
+    # tests/golden/make_golden.py --headline); every rank must reproduce all 16 x 4 words or the run is void
+    golden_cap = headline_golden_cap(n_log, P)
+    if golden_cap is not None:
+        if not np.array_equal(np.asarray(cap_check, dtype=np.uint64), golden_cap):
+            raise SystemExit("bench.py: rank %d: cap of the headline commit differs from the CPU-oracle golden -- run void" % rank)
+        cap_status = "all 16x4 words equal the CPU-oracle golden on every rank"
+    else:
+        cap_status = "no golden for this size (preflight only)"
 
     # ---- timed: device-resident ----
     gpu_index = int(os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",")[local_rank]) if os.environ.get("CUDA_VISIBLE_DEVICES") else local_rank
@@ -314,6 +426,21 @@ def run_b200(args, rank, world, local_rank):
     h2d_bytes = P * n * 8
     d2h_bytes = P * n * 8 + (1 << CAP_HEIGHT) * 32
 
+    ref_cuda = None
+    if rank == 0 and world == 1 and not args.no_ref_cuda and (n_log, P) == (20, 135):
+        # GPU-vs-GPU baseline: the reference's own CUDA kernels (oracle/_ref, compiled unmodified for sm_100a) on the same box
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import ref_cuda_bench
+            r = ref_cuda_bench.measure(n_log, P, reps=2, ctx=ctx, with_ours=False)
+            if "ref_ms" in r:
+                ref_cuda = {"value": r["ref_ms"], "unit": "ms", "kind": "reference CUDA (cuda/plonky2_gpu.cu ifft + merkle_tree_from_coeffs, "
+                            "recompiled unmodified for sm_100a), same B200, device-resident, CUDA events",
+                            "cap_equal": r["ref_cap_word0"] == "%016x" % int(cap_check[0][0])}
+            else:
+                ref_cuda = r
+        except Exception as e:  # the baseline must never take the run down
+            ref_cuda = {"unavailable": repr(e)[:200]}
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         clocks = sampler.summary() if sampler else {}
@@ -335,15 +462,13 @@ def run_b200(args, rank, world, local_rank):
             "metric": METRIC, "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "PolynomialBatch::from_values 2^%d x %d Goldilocks, rate_bits 3, cap_height 4, Poseidon Merkle "
-                                   "(%s)" % (n_log, P, "BASELINE.json configs[1]" if (n_log, P) == (20, 135)
-                                             else "BASELINE.json configs[4] scale sweep: NOT the headline size the metric name quotes"),
+            "config": {"workload": workload_name(n_log, P),
                        "sharding": ("8-column blocks dealt round-robin for the iNTT, one NCCL all-gather per round overlapped with LDE + progressive leaf "
                                     "hashing of the previous round, coset blocks / cap sub-trees per rank") if pipelined
                        else ("columns for iNTT, coset blocks / cap sub-trees for LDE+Merkle" if world > 1 else "single GPU"),
                        "l2": "inputs_exceed_l2 (values %.2f GB, LDE %.2f GB per step vs 126 MB L2)" % (P * n * 8 / 1e9, P * N * 8 / 1e9),
                        "timing": "CUDA events on the library stream around all steps, max over ranks; wall %.1f ms/step" % (wall_ms / args.steps),
-                       "cap_word0": "%016x" % int(cap_check[0][0])},
+                       "cap_word0": "%016x" % int(cap_check[0][0]), "cap_check": cap_status, "parity_preflight": preflight},
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "steps": e2e_steps, "note": "pinned host values -> p2b_commit_from_values -> D2H coefficients + cap; host wall clock, max over ranks"},
             "gpu_launches": launches,
@@ -358,9 +483,13 @@ def run_b200(args, rank, world, local_rank):
                              "instr_per_permutation": INSTR_PER_PERM, "sm_mhz": sm_mhz},
             "clocks": clocks,
         }
+        if ref_cuda is not None:
+            line["ref_cuda_baseline"] = ref_cuda
         if not args.no_cpu_baseline:
-            ms, cores = cpu_commit_ms(args.cpu_sample_log, P, reps=2)
-            line["cpu_baseline"] = cpu_baseline_obj(args, ms * (1 << (n_log - args.cpu_sample_log)), cores)
+            args.cpu_budget_s = min(args.cpu_budget_s, 40.0)
+            sample_log = pick_cpu_sample_log(args, 2)
+            ms, cores = cpu_commit_ms(sample_log, P, reps=2)
+            line["cpu_baseline"] = cpu_baseline_obj(args, ms * (1 << (n_log - sample_log)), cores, sample_log)
         print(json.dumps(line), flush=True)
     host_vals.free()
     host_coef.free()

@@ -15,8 +15,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libplonky2_b200.so")
 SOURCES = ["plonky2_b200.cu"]
-DEPS = ["plonky2_b200.cu", "gl64.cuh", "poseidon.cuh", "poseidon_tables.h", "merkle.cuh", "ntt.cuh", "compat.cuh",
-        "quotient.cuh", "gates.cuh", "../../include/plonky2_b200.h"]
+
+
+def deps():
+    """Every file the translation unit can include: all of csrc/ plus the public header (a stale .so must never pass tests)."""
+    import glob
+    files = []
+    for pat in ("*.cu", "*.cuh", "*.h", "*.hpp"):
+        files += glob.glob(os.path.join(CSRC, pat))
+    files.append(os.path.join(HERE, "..", "include", "plonky2_b200.h"))
+    files.append(os.path.abspath(__file__))
+    return files
 
 
 def nvcc_path():
@@ -30,8 +39,7 @@ def needs_build():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    for d in DEPS:
-        p = os.path.join(CSRC, d)
+    for p in deps():
         if os.path.exists(p) and os.path.getmtime(p) > t:
             return True
     return False

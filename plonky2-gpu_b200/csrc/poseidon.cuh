@@ -61,7 +61,38 @@ __device__ __forceinline__ u64 sbox(u64 x) {
 // out[r] = sum_i circ[i] * s[(i+r)%12] + diag[r]*s[r] + addc[r]   (mds_row_shf + mds_layer, then the next
 // constant_layer folded in).  addc must be canonical round constants (< p).
 __device__ __forceinline__ void mds_layer(u64 (&s)[12], const u64* __restrict__ addc) {
-#ifdef P2B_MDS_LIMB22
+#ifdef P2B_MDS_F64
+  // FP64-pipe form: the 32-bit halves of every word as exact doubles, 12 DFMA per output half accumulated onto
+  // 2^52 + (half of the round constant), so the integer sum sits in the mantissa.
+  double lo[12], hi[12];
+  const double M52 = 4503599627370496.0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    u32 l, h;
+    gl::split(s[i], l, h);
+    lo[i] = __hiloint2double(0x43300000, (int)l) - M52;
+    hi[i] = __hiloint2double(0x43300000, (int)h) - M52;
+  }
+#pragma unroll
+  for (int r = 0; r < 12; r++) {
+    u32 c0, c1;
+    gl::split(addc[r], c0, c1);
+    double al = __hiloint2double(0x43300000, (int)c0), ah = __hiloint2double(0x43300000, (int)c1);
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      al = fma(lo[(i + r) % 12], (double)mds_circ(i), al);
+      ah = fma(hi[(i + r) % 12], (double)mds_circ(i), ah);
+    }
+    if (r == 0) {
+      al = fma(lo[0], (double)MDS_DIAG0, al);
+      ah = fma(hi[0], (double)MDS_DIAG0, ah);
+    }
+    u32 w0 = (u32)__double2loint(al), l1 = (u32)__double2hiint(al), h0 = (u32)__double2loint(ah), h1 = (u32)__double2hiint(ah), w1, w2;
+    asm("{ .reg .u32 t; sub.u32 t, %2, 0x43300000; add.cc.u32 %0, t, %3; .reg .u32 u; sub.u32 u, %4, 0x43300000; addc.u32 %1, u, 0; }"
+        : "=r"(w1), "=r"(w2) : "r"(l1), "r"(h0), "r"(h1));
+    s[r] = gl::reduce96(gl::pack(w0, w1), w2);
+  }
+#elif defined(P2B_MDS_LIMB22)
   // Three 22/22/20-bit limbs per word: every product c*limb and every 12-term sum stays below 2^32, so the whole
   // layer is 32-bit IMAD (64 thread-instr/clk/SM) instead of IMAD.WIDE (~23): 432 IMAD vs 288 IMAD.WIDE.
   u32 x0[12], x1[12], x2[12];

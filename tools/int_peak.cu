@@ -17,8 +17,10 @@ __global__ void __launch_bounds__(256) k(u64* out, u32 a0, u32 b0, long long* cy
   u32 a = a0 + threadIdx.x, b = b0 ^ threadIdx.x;
   u64 acc[NACC];
   u32 r[NACC];
+  double d[NACC];
+  double da = 1.0 + 1e-9 * a0, db = 1e-3 * b0;
 #pragma unroll
-  for (int i = 0; i < NACC; i++) { acc[i] = i * 0x9E3779B97F4A7C15ull + threadIdx.x; r[i] = (u32)acc[i]; }
+  for (int i = 0; i < NACC; i++) { acc[i] = i * 0x9E3779B97F4A7C15ull + threadIdx.x; r[i] = (u32)acc[i]; d[i] = (double)(i + threadIdx.x); }
   __syncthreads();
   long long t0 = clock64();
 #pragma unroll 1
@@ -72,6 +74,78 @@ __global__ void __launch_bounds__(256) k(u64* out, u32 a0, u32 b0, long long* cy
         asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[i]) : "r"(r[(i + 1) % NACC]), "r"(r[(i + 5) % NACC]));
       } else if (KIND == 18) { // IMAD.WIDE multiplying by an immediate with a 64-bit accumulate from another pair
         asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo,hi}, %1; mad.wide.u32 %0, lo, 41, %0; }" : "+l"(acc[i]) : "l"(acc[(i + 1) % NACC]));
+      } else if (KIND == 20) { // DFMA
+        asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(da), "d"(db));
+      } else if (KIND == 21) { // DADD
+        asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(d[i]) : "d"(db));
+      } else if (KIND == 22) { // DMUL
+        asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(d[i]) : "d"(da));
+      } else if (KIND == 23) { // DFMA + IADD3
+        asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(da), "d"(db));
+        asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(r[i]) : "r"(r[(i + 1) % NACC]), "r"(r[(i + 3) % NACC]));
+      } else if (KIND == 24) { // DFMA + IMAD lo
+        asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(da), "d"(db));
+        asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(a), "r"(b));
+      } else if (KIND == 25) { // DFMA + mul.wide (no addend)
+        asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(da), "d"(db));
+        asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo,hi}, %0; mul.wide.u32 %0, lo, %1; }" : "+l"(acc[i]) : "r"(b));
+      } else if (KIND == 26) { // DFMA + mul.wide + IADD3
+        asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(da), "d"(db));
+        asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo,hi}, %0; mul.wide.u32 %0, lo, %1; }" : "+l"(acc[i]) : "r"(b));
+        asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(r[i]) : "r"(r[(i + 1) % NACC]), "r"(r[(i + 3) % NACC]));
+      } else if (KIND == 27) { // DFMA + IMAD lo + IADD3
+        asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(da), "d"(db));
+        asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(a), "r"(b));
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[(i + 4) % NACC]) : "r"(r[(i + 1) % NACC]), "r"(r[(i + 5) % NACC]));
+      } else if (KIND == 28) { // 2 DFMA + mul.wide + 2 ALU
+        asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(da), "d"(db));
+        asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[(i + 4) % NACC]) : "d"(db), "d"(da));
+        asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo,hi}, %0; mul.wide.u32 %0, lo, %1; }" : "+l"(acc[i]) : "r"(b));
+        asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(r[i]) : "r"(r[(i + 1) % NACC]), "r"(r[(i + 3) % NACC]));
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[(i + 4) % NACC]) : "r"(r[(i + 1) % NACC]), "r"(r[(i + 5) % NACC]));
+      } else if (KIND == 29) { // cvt.rn.f64.u32 (I2F.F64.U32)
+        asm volatile("{ .reg .f64 t; cvt.rn.f64.u32 t, %0; mov.b64 {%0, _}, t; }" : "+r"(r[i]));
+      } else if (KIND == 30) { // cvt.rzi.u32.f64 (F2I)
+        asm volatile("{ .reg .u32 t; cvt.rzi.u32.f64 t, %0; mov.b64 %0, {t, t}; }" : "+d"(d[i]));
+      } else if (KIND == 31) { // SEL via setp + selp
+        asm volatile("{ .reg .pred p; setp.lt.u32 p, %0, %1; selp.u32 %0, %1, %2, p; }" : "+r"(r[i]) : "r"(r[(i + 1) % NACC]), "r"(r[(i + 3) % NACC]));
+      } else if (KIND == 32) { // PRMT
+        asm volatile("prmt.b32 %0, %0, %1, 0x3715;" : "+r"(r[i]) : "r"(r[(i + 1) % NACC]));
+      } else if (KIND == 33) { // 32-bit carry chain add.cc / addc (IADD3 + IADD3.X)
+        asm volatile("{ add.cc.u32 %0, %0, %2; addc.u32 %1, %1, %3; }" : "+r"(r[i]), "+r"(r[(i + 4) % NACC]) : "r"(a), "r"(b));
+      } else if (KIND == 34) { // mul.wide + 3 ALU
+        asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo,hi}, %0; mul.wide.u32 %0, lo, %1; }" : "+l"(acc[i]) : "r"(b));
+        asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(r[i]) : "r"(r[(i + 1) % NACC]), "r"(r[(i + 3) % NACC]));
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[i]) : "r"(r[(i + 1) % NACC]), "r"(r[(i + 5) % NACC]));
+        asm volatile("shf.l.wrap.b32 %0, %0, %1, 7;" : "+r"(r[i]) : "r"(a));
+      } else if (KIND == 35) { // IMAD.WIDE addend other pair + 2 ALU
+        asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo,hi}, %0; mad.wide.u32 %0, lo, %1, %2; }" : "+l"(acc[i]) : "r"(b), "l"(acc[(i + 1) % NACC]));
+        asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(r[i]) : "r"(r[(i + 1) % NACC]), "r"(r[(i + 3) % NACC]));
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[i]) : "r"(r[(i + 1) % NACC]), "r"(r[(i + 5) % NACC]));
+      } else if (KIND == 36) { // IMAD.WIDE with 32-bit zero-extended addend in own low word, i.e. acc = lo*b + (u64)r
+        asm volatile("{ .reg .u32 lo, hi; .reg .u64 c; mov.b64 {lo,hi}, %0; cvt.u64.u32 c, %2; mad.wide.u32 %0, lo, %1, c; }" : "+l"(acc[i]) : "r"(b), "r"(r[i]));
+      } else if (KIND == 37) { // DFMA + IMAD.WIDE (addend) 1:1
+        asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(da), "d"(db));
+        asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo,hi}, %0; mad.wide.u32 %0, lo, %1, %0; }" : "+l"(acc[i]) : "r"(b));
+      } else if (KIND == 38) { // 3 DFMA + 1 mul.wide + 2 ALU
+        asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(da), "d"(db));
+        asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[(i + 3) % NACC]) : "d"(db), "d"(da));
+        asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[(i + 5) % NACC]) : "d"(db), "d"(da));
+        asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo,hi}, %0; mul.wide.u32 %0, lo, %1; }" : "+l"(acc[i]) : "r"(b));
+        asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(r[i]) : "r"(r[(i + 1) % NACC]), "r"(r[(i + 3) % NACC]));
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[(i + 4) % NACC]) : "r"(r[(i + 1) % NACC]), "r"(r[(i + 5) % NACC]));
+      } else if (KIND == 39) { // FFMA + IMAD lo + IADD3 (is fmalite a third issue port?)
+        float f = __uint_as_float(r[(i + 2) % NACC]);
+        asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(__uint_as_float(a)), "f"(__uint_as_float(b)));
+        r[(i + 2) % NACC] = __float_as_uint(f);
+        asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(a), "r"(b));
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[(i + 4) % NACC]) : "r"(r[(i + 1) % NACC]), "r"(r[(i + 5) % NACC]));
+      } else if (KIND == 40) { // mul.wide by immediate (no addend)
+        asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo,hi}, %0; mul.wide.u32 %0, lo, 41; }" : "+l"(acc[i]));
+      } else if (KIND == 41) { // IMAD lo with immediate
+        asm volatile("mad.lo.u32 %0, %0, 41, %1;" : "+r"(r[i]) : "r"(b));
+      } else if (KIND == 42) { // IMAD.SHL style: mul.lo by power of two + add (might go ALU as LEA)
+        asm volatile("{ .reg .u32 t; shl.b32 t, %0, 5; add.u32 %0, t, %1; }" : "+r"(r[i]) : "r"(r[(i + 1) % NACC]));
       } else if (KIND == 13) { // mix: 1 IMAD.WIDE + 3 ALU
         asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo,hi}, %0; mad.wide.u32 %0, lo, %1, %0; }" : "+l"(acc[i]) : "r"(b));
         asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(r[i]) : "r"(r[(i + 1) % NACC]), "r"(r[(i + 3) % NACC]));
@@ -83,7 +157,7 @@ __global__ void __launch_bounds__(256) k(u64* out, u32 a0, u32 b0, long long* cy
   long long t1 = clock64();
   u64 s = 0;
 #pragma unroll
-  for (int i = 0; i < NACC; i++) s += acc[i] + r[i];
+  for (int i = 0; i < NACC; i++) s += acc[i] + r[i] + (u64)__double_as_longlong(d[i]);
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
   if (threadIdx.x == 0) {
     u32 smid;
@@ -150,6 +224,30 @@ int main() {
     run<18>("IMAD.WIDE imm, addend other pair", 1, bps);
     run<15>("1 mul.wide + 1 IADD3", 2, bps);
     run<17>("1 mul.wide + 2 ALU", 3, bps);
+
+    run<20>("DFMA", 1, bps);
+    run<21>("DADD", 1, bps);
+    run<22>("DMUL", 1, bps);
+    run<23>("1 DFMA + 1 IADD3", 2, bps);
+    run<24>("1 DFMA + 1 IMAD lo", 2, bps);
+    run<25>("1 DFMA + 1 mul.wide", 2, bps);
+    run<37>("1 DFMA + 1 IMAD.WIDE(addend)", 2, bps);
+    run<26>("1 DFMA + 1 mul.wide + 1 IADD3", 3, bps);
+    run<27>("1 DFMA + 1 IMAD lo + 1 LOP3", 3, bps);
+    run<28>("2 DFMA + 1 mul.wide + 2 ALU", 5, bps);
+    run<38>("3 DFMA + 1 mul.wide + 2 ALU", 6, bps);
+    run<39>("1 FFMA + 1 IMAD lo + 1 LOP3", 3, bps);
+    run<29>("I2F.F64.U32", 1, bps);
+    run<30>("F2I.U32.F64", 1, bps);
+    run<31>("ISETP + SEL", 2, bps);
+    run<32>("PRMT", 1, bps);
+    run<33>("add.cc.u32 + addc.u32", 2, bps);
+    run<34>("1 mul.wide + 3 ALU", 4, bps);
+    run<35>("1 IMAD.WIDE(addend other) + 2 ALU", 3, bps);
+    run<36>("IMAD.WIDE 32-bit addend", 1, bps);
+    run<40>("mul.wide imm", 1, bps);
+    run<41>("IMAD lo imm", 1, bps);
+    run<42>("SHL + IADD (LEA?)", 1, bps);
     printf("\n");
   }
   return 0;
