@@ -35,9 +35,15 @@ import numpy as np  # noqa: E402
 SEED = 0x504C4F4E4B5932
 RATE_BITS, CAP_HEIGHT = 3, 4
 METRIC = "LDE+Merkle commit ms (2^20x135 cols, rate 3)"
-# dynamic thread-instructions of one Poseidon permutation in the shipped SASS (tools/sass_mix.py / ncu
-# smsp__inst_executed of hash_leaves_kernel divided by permutations; profiles/README.md)
-INSTR_PER_PERM = 21830
+# dynamic thread-instructions of one Poseidon permutation in the shipped SASS: ncu "Instructions Executed" per SASS line of
+# hash_leaves_kernel (tools/ncu_opmix.py) divided by the permutations, profiles/r02_hash_leaves_ncu.md
+INSTR_PER_PERM = 16100
+WIDE_PER_PERM = 2878    # IMAD.WIDE.U32 (all forms)
+FP64_PER_PERM = 5463    # DADD + DFMA
+# measured issue costs per warp-instruction (tools/int_peak.cu "clean mixes", profiles/r02_pipe_model.md): IMAD.WIDE 4.36
+# cycles, FP64 2.2 cycles, and the two do NOT overlap (W + kD costs 4.36 + 2.2 k), while ALU / 32-bit IMAD / XU work does
+WIDE_CYCLES, FP64_CYCLES = 4.36, 2.2
+MIXED_INT_LANES_PER_CLK_PER_SM = 119.6  # IADD3 + IMAD.X on both integer pipes (profiles/int_peak_r01.md)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE leaf-hash launch (2^20 leaves x 135) from the committed
 # `ncu --set full` capture, profiles/r01b_hash_leaves_ncu.md
 HASH_LAUNCH_DRAM_BYTES_2P20_X135 = 1254320000 + 43090688
@@ -432,7 +438,19 @@ def run_b200(args, rank, world, local_rank):
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import ref_cuda_bench
-            r = ref_cuda_bench.measure(n_log, P, reps=2, ctx=ctx, with_ours=False)
+            # the reference kernels printf their own timings: keep them off this process's stdout (ONE JSON line)
+            sys.stdout.flush()
+            saved_fd = os.dup(1)
+            devnull = os.open(os.devnull, os.O_WRONLY)
+            os.dup2(devnull, 1)
+            try:
+                r = ref_cuda_bench.measure(n_log, P, reps=2, ctx=ctx, with_ours=False)
+            finally:
+                import ctypes
+                ctypes.CDLL(None).fflush(None)
+                os.dup2(saved_fd, 1)
+                os.close(saved_fd)
+                os.close(devnull)
             if "ref_ms" in r:
                 ref_cuda = {"value": r["ref_ms"], "unit": "ms", "kind": "reference CUDA (cuda/plonky2_gpu.cu ifft + merkle_tree_from_coeffs, "
                             "recompiled unmodified for sm_100a), same B200, device-resident, CUDA events",
@@ -458,6 +476,9 @@ def run_b200(args, rank, world, local_rank):
         sm_mhz = clocks.get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
         int_peak = INT_LANES_PER_CLK_PER_SM * 148 * sm_mhz * 1e6          # thread-instructions / s
         int_ach = perms_per_launch * INSTR_PER_PERM / (avg_hash_ms * 1e-3) if avg_hash_ms > 0 else 0.0
+        perm_rate = perms_per_launch / (avg_hash_ms * 1e-3) if avg_hash_ms > 0 else 0.0
+        heavy_cycles = WIDE_PER_PERM * WIDE_CYCLES + FP64_PER_PERM * FP64_CYCLES       # per warp (32 permutations), per sub-partition
+        heavy_peak = 148 * 4 * sm_mhz * 1e6 * 32 / heavy_cycles                         # permutations / s if that resource never idled
         line = {
             "metric": METRIC, "value": ms_per_step, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
@@ -477,10 +498,14 @@ def run_b200(args, rank, world, local_rank):
                          "traffic": HASH_LAUNCH_DRAM_BYTES_2P20_X135 if (n_log == 20 and P == 135 and not pipelined) else None, "peak_source": peak_kind + " (burst copy bandwidth)",
                          "launches_timed": hash_launches, "avg_launch_ms": avg_hash_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "share_of_step": hash_ms / max(dev_ms, 1e-9)},
-            "roofline_int": {"bound": "integer issue (64 INT32 lanes/clk/SM measured)", "achieved": int_ach / 1e12, "peak": int_peak / 1e12,
-                             "unit": "T thread-instr/s", "frac": int_ach / int_peak if int_peak else None,
-                             "perm_per_s": perms_per_launch / (avg_hash_ms * 1e-3) if avg_hash_ms > 0 else None,
-                             "instr_per_permutation": INSTR_PER_PERM, "sm_mhz": sm_mhz},
+            "roofline_int": {"bound": "IMAD.WIDE + FP64 issue cycles (mutually exclusive on sm_100a, measured): the binding resource of "
+                                      "the Poseidon kernel", "achieved": perm_rate / 1e6, "peak": heavy_peak / 1e6, "unit": "Mperm/s",
+                             "frac": perm_rate / heavy_peak if heavy_peak else None,
+                             "cycles_per_warp_permutation": heavy_cycles, "wide_per_permutation": WIDE_PER_PERM,
+                             "fp64_per_permutation": FP64_PER_PERM, "instr_per_permutation": INSTR_PER_PERM, "sm_mhz": sm_mhz,
+                             "thread_instr_per_s_T": int_ach / 1e12,
+                             "frac_of_64_lane_single_pipe": int_ach / int_peak if int_peak else None,
+                             "frac_of_mixed_alu_fma_119.6_lanes": int_ach / (int_peak * MIXED_INT_LANES_PER_CLK_PER_SM / INT_LANES_PER_CLK_PER_SM) if int_peak else None},
             "clocks": clocks,
         }
         if ref_cuda is not None:

@@ -83,29 +83,6 @@ __device__ __forceinline__ void mul_wide(u64 a, u64 b, u64& lo, u64& hi) {
 //          r + eps (mod 2^64) is the answer whether or not the subtraction borrowed.
 //   c = 0, b = 1: true value is negative; r wrapped by +2^64, repay with -eps (cannot underflow).
 __device__ __forceinline__ u64 reduce128(u64 lo, u64 hi) {
-#ifdef P2B_REDUCE_ALU
-  // ALU-only form (no IMAD.WIDE, which is the scarce issue slot on sm_100a: ~23 thread-instr/clk/SM against 64
-  // for IADD3):  x == lo - h0 - h1 + (h0 << 32); the 64-bit adder wraps k times (k in {-1,0,1}), repaid by k*eps.
-  u32 l0, l1, h0, h1, t0, t1, k;
-  split(lo, l0, l1);
-  split(hi, h0, h1);
-  asm("{\n\t"
-      "sub.cc.u32 %0, %3, %5;\n\t"
-      "subc.cc.u32 %1, %4, 0;\n\t"
-      "subc.u32 %2, 0, 0;\n\t"
-      "sub.cc.u32 %0, %0, %6;\n\t"
-      "subc.cc.u32 %1, %1, 0;\n\t"
-      "subc.u32 %2, %2, 0;\n\t"
-      "add.cc.u32 %1, %1, %5;\n\t"
-      "addc.u32 %2, %2, 0;\n\t"
-      "}"
-      : "=&r"(t0), "=&r"(t1), "=&r"(k)
-      : "r"(l0), "r"(l1), "r"(h0), "r"(h1));
-  // k*eps as a 64-bit two's complement number: k = 1 -> (0xffffffff, 0); k = -1 -> (1, 0xffffffff)
-  u32 a0 = 0u - k, a1 = (u32)((int)k >> 31), r0, r1;
-  asm("{ add.cc.u32 %0, %2, %4; addc.u32 %1, %3, %5; }" : "=&r"(r0), "=&r"(r1) : "r"(t0), "r"(t1), "r"(a0), "r"(a1));
-  return pack(r0, r1);
-#else
   u32 h0, h1;
   split(hi, h0, h1);
   u64 y, r;
@@ -117,7 +94,6 @@ __device__ __forceinline__ u64 reduce128(u64 lo, u64 hi) {
   r = (u64)c * EPS + r;            // arithmetic mod 2^64 is intended
   u32 k = w & (c - 1u);            // 0xffffffff iff (b && !c)
   return r - (u64)k;               // - eps
-#endif
 }
 
 __device__ __forceinline__ u64 mul(u64 a, u64 b) {
@@ -180,30 +156,12 @@ __device__ __forceinline__ u64 mul_add(u64 a, u64 b, u64 c) {
 
 // from_noncanonical_u96 (goldilocks_field.rs:153-165): lo + 2^64*hi32
 __device__ __forceinline__ u64 reduce96(u64 lo, u32 hi) {
-#ifdef P2B_REDUCE_ALU
-  // lo + hi*eps = lo - hi + (hi << 32): at most one net wrap, k in {-1, 0, 1}
-  u32 l0, l1, t0, t1, k;
-  split(lo, l0, l1);
-  asm("{\n\t"
-      "sub.cc.u32 %0, %3, %5;\n\t"
-      "subc.cc.u32 %1, %4, 0;\n\t"
-      "subc.u32 %2, 0, 0;\n\t"
-      "add.cc.u32 %1, %1, %5;\n\t"
-      "addc.u32 %2, %2, 0;\n\t"
-      "}"
-      : "=&r"(t0), "=&r"(t1), "=&r"(k)
-      : "r"(l0), "r"(l1), "r"(hi));
-  u32 a0 = 0u - k, a1 = (u32)((int)k >> 31), r0, r1;
-  asm("{ add.cc.u32 %0, %2, %4; addc.u32 %1, %3, %5; }" : "=&r"(r0), "=&r"(r1) : "r"(t0), "r"(t1), "r"(a0), "r"(a1));
-  return pack(r0, r1);
-#else
   u64 y;
   u32 c;
   asm("{ .reg .u64 m; mul.wide.u32 m, %2, 0xffffffff; add.cc.u64 %0, m, %3; addc.u32 %1, 0, 0; }"
       : "=l"(y), "=r"(c)
       : "r"(hi), "l"(lo));
   return (u64)c * EPS + y;
-#endif
 }
 
 // x^e by square-and-multiply (exp_u64, field/src/types.rs:347-371)

@@ -2,21 +2,29 @@
 // overwrite-mode sponge / 2-to-1 compression built on it, for sm_100a.
 //
 // What is computed (bit-exact with the reference CPU path):
-//   permute()        Poseidon::poseidon            plonky2/src/hash/poseidon.rs:590-606
-//   full round       constant_layer/sbox/mds_layer poseidon.rs:482-493, 525-548, 172-260
-//   partial rounds   "fast" form                   poseidon.rs:574-588 with :310-365 (first-round constants +
-//                                                  11x11 initial matrix) and :398-427 (W_HATS / VS layer)
+//   permute()        Poseidon::poseidon            plonky2/src/hash/poseidon.rs:590-606, evaluated in the algebraically
+//                                                  identical "naive" round structure poseidon_naive (poseidon.rs:619-640):
+//                                                  30 x [constant_layer, S-box (all lanes | lane 0), mds_layer]
+//   S-box            sbox_monomial                 poseidon.rs:525-548
+//   MDS layer        mds_row_shf / mds_layer       poseidon.rs:172-260
+//   fast partial rounds (kept for the Poseidon GATE evaluator, whose wires are defined in that basis, quotient.cuh)
+//                                                  poseidon.rs:310-365, 398-427, 574-588
 //   hash_or_noop / hash_no_pad / two_to_one        plonk/config.rs:56-67, hash/hashing.rs:81-104, :65-72
 //
-// How (B200): the 12-word state lives in registers (24 x 32-bit); a full round's MDS works on the 32-bit
-// halves of each word with IMAD.WIDE.U32 multiply-accumulates by the <=6-bit circulant entries (immediates
-// in the instruction stream), sums both halves in 64-bit accumulators (no carries possible: 12 * 41 * 2^32
-// < 2^42), adds the NEXT round's constant into the 96-bit sum and reduces once.  S-boxes are 4 mod-muls of
-// gl::mul (4 IMAD.WIDE + reduce).  Round loops are kept rolled (#pragma unroll 1) so the hot loop bodies
-// (~1.2k instructions for a full round, ~0.5k for a partial round) stay inside the instruction cache;
-// per-round constants are fetched from __constant__ memory (uniform across the warp -> LDC broadcast).
+// How (B200).  Measured on the box (profiles/r02_pipe_model.md): IMAD.WIDE.U32 costs ~4.3 issue cycles per warp on the
+// FMA-heavy pipe and cannot overlap FP64 instructions; IADD3/LOP3 (ALU), 32-bit IMAD and DADD/DFMA (FP64, 64 lanes/clk/SM
+// on B200) cost ~2 cycles each on three pipes that do overlap.  The reference's fast partial rounds trade one small-
+// constant MDS layer for 22 dense 64x64-bit multiplications, which is the right trade on a CPU and the wrong one here:
+// a dense multiplication is 6 IMAD.WIDE, while the MDS layer needs NO multiplier at all -- its circulant becomes, by the
+// Chinese remainder theorem over t^12 - 1, 78 additions / multiply-adds by +-2^k (mds_fft.cuh), run exactly on the FP64
+// pipe over the 32-bit halves of the state words.  So every round is evaluated in the naive form: S-boxes as 64-bit
+// modular multiplications (gl64.cuh, optimistic reduction with an exact redo), the linear layer in doubles, the next
+// round's constants folded into the double -> integer conversion.  Per permutation: 16.1 k thread-instructions
+// (2.9 k IMAD.WIDE, 5.5 k FP64) against 21.8 k (8.7 k IMAD.WIDE) for the fast form of round 1.
 #pragma once
+#include <string.h>
 #include "gl64.cuh"
+#include "mds_fft.cuh"
 #include "poseidon_tables.h"
 
 namespace poseidon {
@@ -34,6 +42,8 @@ struct Consts {
   u64 init[11 * 11];  // FAST_PARTIAL_ROUND_INITIAL_MATRIX  [r-1][c-1]
   u64 post[8 * 12];   // constants added right after the MDS of full round k (k = 0..7): rows 1,2,3 of rc,
                       // first_rc, rows 27,28,29 of rc, zeros  (next round's constant_layer folded forward)
+  double rc_d[31 * 12 * 2];   // 2^52 + low half, 2^52 + high half of ALL_ROUND_CONSTANTS row r (row 30 = zeros): the constant
+                              // layer of round r rides on the double -> integer conversion after the MDS of round r - 1
 };
 // The library is a single translation unit (plonky2_b200.cu), so the definition lives here.
 __constant__ Consts C;
@@ -58,84 +68,38 @@ __device__ __forceinline__ u64 sbox(u64 x) {
   return sbox(x, m);
 }
 
+// (2^52 + L, 2^52 + H) with integers 0 <= L, H < 2^51  ->  a u64 representative of L + 2^32 * H  (mod p).
+// The integers sit in the mantissas: low word = bits 0..31, high word = 0x43300000 + bits 32..51.
+__device__ __forceinline__ u64 from_biased_halves(double al, double ah) {
+  u32 w0 = (u32)__double2loint(al), l1 = (u32)__double2hiint(al), h0 = (u32)__double2loint(ah), h1 = (u32)__double2hiint(ah), w1, w2;
+  asm("{ .reg .u32 t, u; sub.u32 t, %2, 0x43300000; add.cc.u32 %0, t, %3; sub.u32 u, %4, 0x43300000; addc.u32 %1, u, 0; }"
+      : "=r"(w1), "=r"(w2) : "r"(l1), "r"(h0), "r"(h1));
+  return gl::reduce96(gl::pack(w0, w1), w2);
+}
+
+// Optimistic form without any multiply: with L = l0 + 2^32 l1, H = h0 + 2^32 h1 (l1, h1 < 2^19) and 2^64 == 2^32 - 1,
+//   L + 2^32 H  ==  (l0 - h1) + 2^32 (h0 + l1 + h1)   (mod p);
+// the middle sum overflows 32 bits with probability ~2^-22 -- that case is flagged in m.rare and the caller redoes its
+// work with the exact functions (the borrow of l0 - h1 is propagated exactly; it can only underflow the high word
+// together with the flagged overflow).  6 ALU instructions instead of 2 IMAD.WIDE + 4.
+template <class M>
+__device__ __forceinline__ u64 from_biased_halves(double al, double ah, M& m) {
+  if (M::optimistic) {
+    u32 l0 = (u32)__double2loint(al), hl = (u32)__double2hiint(al), h0 = (u32)__double2loint(ah), hh = (u32)__double2hiint(ah);
+    u32 u = hl + hh - 0x86600000u;   // l1 + h1
+    u32 h1 = hh - 0x43300000u;
+    u32 mid = h0 + u;
+    m.rare |= mid < u;
+    u32 lo, hi;
+    asm("{ sub.cc.u32 %0, %2, %3; subc.u32 %1, %4, 0; }" : "=r"(lo), "=r"(hi) : "r"(l0), "r"(h1), "r"(mid));
+    return gl::pack(lo, hi);
+  }
+  return from_biased_halves(al, ah);
+}
+
 // out[r] = sum_i circ[i] * s[(i+r)%12] + diag[r]*s[r] + addc[r]   (mds_row_shf + mds_layer, then the next
 // constant_layer folded in).  addc must be canonical round constants (< p).
 __device__ __forceinline__ void mds_layer(u64 (&s)[12], const u64* __restrict__ addc) {
-#ifdef P2B_MDS_F64
-  // FP64-pipe form: the 32-bit halves of every word as exact doubles, 12 DFMA per output half accumulated onto
-  // 2^52 + (half of the round constant), so the integer sum sits in the mantissa.
-  double lo[12], hi[12];
-  const double M52 = 4503599627370496.0;
-#pragma unroll
-  for (int i = 0; i < 12; i++) {
-    u32 l, h;
-    gl::split(s[i], l, h);
-    lo[i] = __hiloint2double(0x43300000, (int)l) - M52;
-    hi[i] = __hiloint2double(0x43300000, (int)h) - M52;
-  }
-#pragma unroll
-  for (int r = 0; r < 12; r++) {
-    u32 c0, c1;
-    gl::split(addc[r], c0, c1);
-    double al = __hiloint2double(0x43300000, (int)c0), ah = __hiloint2double(0x43300000, (int)c1);
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-      al = fma(lo[(i + r) % 12], (double)mds_circ(i), al);
-      ah = fma(hi[(i + r) % 12], (double)mds_circ(i), ah);
-    }
-    if (r == 0) {
-      al = fma(lo[0], (double)MDS_DIAG0, al);
-      ah = fma(hi[0], (double)MDS_DIAG0, ah);
-    }
-    u32 w0 = (u32)__double2loint(al), l1 = (u32)__double2hiint(al), h0 = (u32)__double2loint(ah), h1 = (u32)__double2hiint(ah), w1, w2;
-    asm("{ .reg .u32 t; sub.u32 t, %2, 0x43300000; add.cc.u32 %0, t, %3; .reg .u32 u; sub.u32 u, %4, 0x43300000; addc.u32 %1, u, 0; }"
-        : "=r"(w1), "=r"(w2) : "r"(l1), "r"(h0), "r"(h1));
-    s[r] = gl::reduce96(gl::pack(w0, w1), w2);
-  }
-#elif defined(P2B_MDS_LIMB22)
-  // Three 22/22/20-bit limbs per word: every product c*limb and every 12-term sum stays below 2^32, so the whole
-  // layer is 32-bit IMAD (64 thread-instr/clk/SM) instead of IMAD.WIDE (~23): 432 IMAD vs 288 IMAD.WIDE.
-  u32 x0[12], x1[12], x2[12];
-#pragma unroll
-  for (int i = 0; i < 12; i++) {
-    u32 lo, hi;
-    gl::split(s[i], lo, hi);
-    x0[i] = lo & 0x3fffffu;
-    x1[i] = __funnelshift_r(lo, hi, 22) & 0x3fffffu;
-    x2[i] = hi >> 12;
-  }
-#pragma unroll
-  for (int r = 0; r < 12; r++) {
-    u32 s0 = 0, s1 = 0, s2 = 0;
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-      s0 += x0[(i + r) % 12] * mds_circ(i);
-      s1 += x1[(i + r) % 12] * mds_circ(i);
-      s2 += x2[(i + r) % 12] * mds_circ(i);
-    }
-    if (r == 0) {
-      s0 += x0[0] * MDS_DIAG0;
-      s1 += x1[0] * MDS_DIAG0;
-      s2 += x2[0] * MDS_DIAG0;
-    }
-    // value = s0 + s1*2^22 + s2*2^44 + addc[r]  ->  (w0, w1, w2)
-    u32 c0, c1, w0, w1, w2;
-    gl::split(addc[r], c0, c1);
-    u32 a_lo = s1 << 22, a_hi = s1 >> 10;   // s1 * 2^22 as (lo, hi)
-    u32 b_lo = s2 << 12, b_hi = s2 >> 20;   // s2 * 2^44 as (mid, top)
-    asm("{\n\t"
-        "add.cc.u32 %0, %3, %4;\n\t"        // w0 = s0 + a_lo
-        "addc.cc.u32 %1, %5, %6;\n\t"       // w1 = a_hi + b_lo + c
-        "addc.u32 %2, %7, 0;\n\t"           // w2 = b_hi + c
-        "add.cc.u32 %0, %0, %8;\n\t"        // + round constant
-        "addc.cc.u32 %1, %1, %9;\n\t"
-        "addc.u32 %2, %2, 0;\n\t"
-        "}"
-        : "=&r"(w0), "=&r"(w1), "=&r"(w2)
-        : "r"(s0), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(c0), "r"(c1));
-    s[r] = gl::reduce96(gl::pack(w0, w1), w2);
-  }
-#else
   u32 lo[12], hi[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) gl::split(s[i], lo[i], hi[i]);
@@ -170,19 +134,18 @@ __device__ __forceinline__ void mds_layer(u64 (&s)[12], const u64* __restrict__ 
     }
     s[r] = gl::reduce96(gl::pack(w0, w1), w2);
   }
-#endif
 }
 
-// sbox_layer (poseidon.rs:534-548).  Code size matters more than instruction count here: with ~28 warps per SM
-// streaming through the permutation, instruction fetch stalls ("no_instruction" in ncu) dominate as soon as the
-// hot code exceeds the ~32 KB instruction cache, so the 12 S-boxes are a rolled loop of 3 x 4 with a register
-// rotation (24 moves per iteration) instead of 12 inlined copies (13 KB of SASS).
+// sbox_layer (poseidon.rs:534-548).  Two forms: the hash kernels inline all 12 S-boxes (no register moves; their round
+// loop is small since the MDS layer shrank to ~350 instructions); the gate evaluator (quotient.cuh), whose kernel is
+// instruction-cache bound, uses the rolled 3 x 4 form with a register rotation.
 template <class M>
 __device__ __forceinline__ void sbox_layer(u64 (&s)[12], M& m) {
-#ifdef P2B_SBOX_UNROLLED
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = sbox(s[i], m);
-#else
+}
+template <class M>
+__device__ __forceinline__ void sbox_layer_rolled(u64 (&s)[12], M& m) {
 #pragma unroll 1
   for (int g = 0; g < 3; g++) {
     u64 t0 = sbox(s[0], m), t1 = sbox(s[1], m), t2 = sbox(s[2], m), t3 = sbox(s[3], m);
@@ -193,12 +156,6 @@ __device__ __forceinline__ void sbox_layer(u64 (&s)[12], M& m) {
     s[10] = t2;
     s[11] = t3;
   }
-#endif
-}
-
-__device__ __forceinline__ void sbox_layer(u64 (&s)[12]) {
-  gl::Exact m;
-  sbox_layer(s, m);
 }
 
 // 128-bit accumulate helper for the partial-round dot products: (acc_lo, acc_hi, acc_top) += a*b
@@ -218,35 +175,11 @@ __device__ __forceinline__ u64 reduce160(u64 lo, u64 hi, u32 top) {
   return reduce160(lo, hi, top, m);
 }
 
-// Optional block-wide barrier at every round boundary (P2B_SYNC_ROUNDS): keeps all warps of a CTA inside the same
-// loop body so they share instruction-cache lines (the unrolled round bodies are 8-20 KB each and ncu shows
-// "no_instruction" as the top stall when warps drift apart).  Only legal when every thread of the CTA runs the
-// same number of permutations -- the kernels that enable it keep their tail threads alive on clamped indices.
-__device__ __forceinline__ void round_sync() {
-#ifdef P2B_SYNC_ROUNDS
-  __syncthreads();
-#endif
-}
-
 // mds_partial_layer_init (poseidon.rs:310-337): s[0] unchanged; s[c] = sum_r s[r] * init[r-1][c-1].
 // Rolled over the output column c (keeps ~24 KB of straight-line code out of the instruction cache); the results
 // are pushed through a shift register so no register array is indexed dynamically.
 template <class M>
 __device__ __forceinline__ void partial_layer_init(u64 (&s)[12], M& m) {
-#ifdef P2B_INIT_UNROLLED
-  u64 t[12];
-  t[0] = s[0];
-#pragma unroll
-  for (int c = 1; c < 12; c++) {
-    u64 lo = 0, hi = 0;
-    u32 top = 0;
-#pragma unroll
-    for (int r = 1; r < 12; r++) mac160(lo, hi, top, s[r], C.init[(r - 1) * 11 + (c - 1)]);
-    t[c] = reduce160(lo, hi, top, m);
-  }
-#pragma unroll
-  for (int i = 0; i < 12; i++) s[i] = t[i];
-#else
   u64 t[12];
 #pragma unroll
   for (int i = 1; i < 12; i++) t[i] = 0;
@@ -263,7 +196,6 @@ __device__ __forceinline__ void partial_layer_init(u64 (&s)[12], M& m) {
   }
 #pragma unroll
   for (int i = 1; i < 12; i++) s[i] = t[i];
-#endif
 }
 
 // mds_partial_layer_fast (poseidon.rs:398-427) for partial round r; s0 = the S-boxed (and constant-added) lane 0:
@@ -299,35 +231,39 @@ __device__ __forceinline__ void partial_layer_fast(u64 (&s)[12], u64 s0, int r) 
   partial_layer_fast(s, s0, r, m);
 }
 
-// The permutation.  Input: any u64 representatives; output: u64 representatives (NOT canonicalised --
-// callers canonicalise what they store).
+// ---- the permutation ---------------------------------------------------------------------------------------------------
+// One MDS layer in the naive round structure + the NEXT round's constant layer: bias[2r], bias[2r+1] = 2^52 + the halves of
+// that constant, so "add the constant" and "move the integer into the mantissa" are the same DADD.
+template <class M>
+__device__ __forceinline__ void mds_naive(u64 (&s)[12], const double* __restrict__ bias, M& m) {
+  double lo[12], hi[12], yl[12], yh[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    u32 l, h;
+    gl::split(s[i], l, h);
+    lo[i] = __uint2double_rn(l);   // I2F.F64.U32: exact, and on the otherwise idle XU pipe
+    hi[i] = __uint2double_rn(h);
+  }
+  mdsfft::mds12<double>(lo, yl);
+  mdsfft::mds12<double>(hi, yh);
+#pragma unroll
+  for (int r = 0; r < 12; r++) s[r] = from_biased_halves(yl[r] + bias[2 * r], yh[r] + bias[2 * r + 1], m);
+}
+
+// Input: any u64 representatives; output: u64 representatives (NOT canonicalised -- callers canonicalise what they store).
 template <class M>
 __device__ __forceinline__ void permute(u64 (&s)[12], M& m) {
-  // constant layer of round 0 up front; every later constant layer is folded into the preceding MDS.
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl::add_canonical(s[i], C.rc[i]);
 #pragma unroll 1
-  for (int half = 0; half < 2; half++) {
-    // ---- 4 full rounds (poseidon.rs:560-572) ----
-#pragma unroll 1
-    for (int r = 0; r < 4; r++) {
-      round_sync();
-      sbox_layer(s, m);
-      mds_layer(s, &C.post[12 * (half * 4 + r)]);
-    }
-    if (half == 0) {
-      // ---- partial rounds (poseidon.rs:574-588); first-round constants were folded into post[3] ----
-      partial_layer_init(s, m);
-#pragma unroll 1
-      for (int r = 0; r < 22; r++) {
-        round_sync();
-        u64 s0 = gl::add_canonical(sbox(s[0], m), C.partial_rc[r]);
-        partial_layer_fast(s, s0, r, m);
-      }
-      // constant layer of round 26 (first of the closing full rounds)
-#pragma unroll
-      for (int i = 0; i < 12; i++) s[i] = gl::add_canonical(s[i], C.rc[12 * 26 + i]);
-    }
+  for (int r = 0; r < 30; r++) {
+#ifndef P2B_LAB_NOSBOX   // (timing experiments only: tools/poseidon_lab.cu)
+    if (r < 4 || r >= 26) sbox_layer(s, m);
+    else s[0] = sbox(s[0], m);
+#endif
+#ifndef P2B_LAB_NOMDS
+    mds_naive(s, C.rc_d + 24 * (r + 1), m);
+#endif
   }
 }
 
@@ -370,6 +306,17 @@ inline cudaError_t upload_constants() {
       else v = 0;
       h.post[12 * k + i] = v;
     }
+  auto biased = [](u32 half) {
+    u64 bits = 0x4330000000000000ull | (u64)half;  // 2^52 + half, exactly
+    double d;
+    memcpy(&d, &bits, 8);
+    return d;
+  };
+  for (int i = 0; i < 31 * 12; i++) {
+    u64 v = i < 360 ? P2_ROUND_CONSTANTS[i] : 0;
+    h.rc_d[2 * i] = biased((u32)v);
+    h.rc_d[2 * i + 1] = biased((u32)(v >> 32));
+  }
   return cudaMemcpyToSymbol(C, &h, sizeof(h));
 }
 

@@ -441,7 +441,7 @@ __device__ __forceinline__ void eval_poseidon(const u64* w, E& e) {
         s[8] = v0; s[9] = v1; s[10] = v2; s[11] = v3;
       }
     }
-    sbox_layer(s, e.mode);
+    sbox_layer_rolled(s, e.mode);
     mds_layer(s, &C.post[12 * r]);  // + constants of the next full round / first partial constants after r = 3
   }
   partial_layer_init(s, e.mode);
@@ -469,7 +469,7 @@ __device__ __forceinline__ void eval_poseidon(const u64* w, E& e) {
       for (int i = 0; i < 8; i++) s[i] = s[i + 4];
       s[8] = v0; s[9] = v1; s[10] = v2; s[11] = v3;
     }
-    sbox_layer(s, e.mode);
+    sbox_layer_rolled(s, e.mode);
     mds_layer(s, &C.post[12 * (4 + r)]);
   }
 #pragma unroll 1

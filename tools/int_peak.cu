@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 typedef uint32_t u32;
 typedef uint64_t u64;
 
@@ -146,6 +147,18 @@ __global__ void __launch_bounds__(256) k(u64* out, u32 a0, u32 b0, long long* cy
         asm volatile("mad.lo.u32 %0, %0, 41, %1;" : "+r"(r[i]) : "r"(b));
       } else if (KIND == 42) { // IMAD.SHL style: mul.lo by power of two + add (might go ALU as LEA)
         asm volatile("{ .reg .u32 t; shl.b32 t, %0, 5; add.u32 %0, t, %1; }" : "+r"(r[i]) : "r"(r[(i + 1) % NACC]));
+      } else if (KIND >= 100 && KIND < 200) {
+        // clean mixes (SASS-verified): KIND = 100 + 16*W + 4*D + A  with W in {0: none, 1: mul.wide(+LOP3 keeping both halves live), 2: IMAD lo}, D = #DFMA (0..3), A = #extra LOP3 (0..3)
+        const int W = (KIND - 100) / 16, D = ((KIND - 100) / 4) % 4, A = (KIND - 100) % 4;
+        if (W == 1) {
+          u32 lo, hi;
+          asm volatile("{ .reg .u64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0,%1}, t; }" : "=r"(lo), "=r"(hi) : "r"(r[i]), "r"(b));
+          asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r[i]) : "r"(lo), "r"(hi), "r"(a));
+        } else if (W == 2) {
+          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(a), "r"(b));
+        }
+        for (int q = 0; q < D; q++) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[(i + 3 * q) % NACC]) : "d"(da), "d"(db));
+        for (int q = 0; q < A; q++) { u32 lo_, hi_; asm volatile("mov.b64 {%0,%1}, %2;" : "=r"(lo_), "=r"(hi_) : "l"(acc[(i + q) % NACC])); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(lo_) : "r"(hi_), "r"(b)); asm volatile("mov.b64 %0, {%1,%2};" : "=l"(acc[(i + q) % NACC]) : "r"(lo_), "r"(hi_)); }
       } else if (KIND == 13) { // mix: 1 IMAD.WIDE + 3 ALU
         asm volatile("{ .reg .u32 lo, hi; mov.b64 {lo,hi}, %0; mad.wide.u32 %0, lo, %1, %0; }" : "+l"(acc[i]) : "r"(b));
         asm volatile("{ .reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2; }" : "+r"(r[i]) : "r"(r[(i + 1) % NACC]), "r"(r[(i + 3) % NACC]));
@@ -203,8 +216,8 @@ void run(const char* name, int instr_per_slot, int blocks_per_sm) {
   free(h); cudaFree(out); cudaFree(cyc);
 }
 
-int main() {
-  for (int bps = 8; bps <= 8; bps *= 2) {
+int main(int argc, char** argv) {
+  for (int bps = (argc > 1 ? atoi(argv[1]) : 8); bps <= (argc > 1 ? atoi(argv[1]) : 8); bps *= 2) {
     run<0>("IMAD.WIDE.U32", 1, bps);
     run<9>("IMAD.WIDE.U32 imm", 1, bps);
     run<1>("IMAD (lo)", 1, bps);
@@ -248,6 +261,25 @@ int main() {
     run<40>("mul.wide imm", 1, bps);
     run<41>("IMAD lo imm", 1, bps);
     run<42>("SHL + IADD (LEA?)", 1, bps);
+
+    printf("-- clean mixes: W=mul.wide(+1 LOP3), I=IMAD lo, D=DFMA, A=LOP3\n");
+    run<100 + 16 * 1>("W(+L)", 2, bps);
+    run<100 + 16 * 1 + 4 * 1>("W(+L) + 1D", 3, bps);
+    run<100 + 16 * 1 + 4 * 2>("W(+L) + 2D", 4, bps);
+    run<100 + 16 * 1 + 4 * 3>("W(+L) + 3D", 5, bps);
+    run<100 + 16 * 1 + 2>("W(+L) + 2A", 4, bps);
+    run<100 + 16 * 1 + 4 * 2 + 2>("W(+L) + 2D + 2A", 6, bps);
+    run<100 + 4 * 1>("1D", 1, bps);
+    run<100 + 4 * 2>("2D", 2, bps);
+    run<100 + 4 * 2 + 2>("2D + 2A", 4, bps);
+    run<100 + 4 * 1 + 1>("1D + 1A", 2, bps);
+    run<100 + 2>("2A", 2, bps);
+    run<100 + 16 * 2>("I", 1, bps);
+    run<100 + 16 * 2 + 4 * 1>("I + 1D", 2, bps);
+    run<100 + 16 * 2 + 4 * 2>("I + 2D", 3, bps);
+    run<100 + 16 * 2 + 1>("I + 1A", 2, bps);
+    run<100 + 16 * 2 + 4 * 1 + 1>("I + 1D + 1A", 3, bps);
+    run<100 + 16 * 2 + 4 * 2 + 2>("I + 2D + 2A", 5, bps);
     printf("\n");
   }
   return 0;
