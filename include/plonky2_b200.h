@@ -15,7 +15,7 @@
  *      compute_quotient_polys (plonky2/src/plonk/prover.rs:790-1034) for any (rows, columns, rate_bits,
  *      cap_height, gate set).
  *   2. The reference's own six symbols (`init`, `ifft`, `build_merkle_tree`, `merkle_tree_from_values`,
- *      `merkle_tree_from_coeffs`, `compute_quotient_polys`) plus `transpose`/`fft_blinding`, with the
+ *      `merkle_tree_from_coeffs`, `compute_quotient_polys`) plus `transpose` and `fft_blinding`, with the
  *      reference's exact signatures, in-place device-memory layout and by-value error struct, so
  *      cuda/src/lib.rs links against this library unchanged.  See INTEGRATION.md.
  *
@@ -358,6 +358,11 @@ p2b_rust_error merkle_tree_from_coeffs(uint64_t* d_values_flatten, uint64_t* d_e
                                        void* ctx); /* lib.rs:100-114 */
 p2b_rust_error transpose(uint64_t* d_ext_values_flatten, int poly_num, int values_num_per_poly, int rate_bits,
                          int salt_size, int pad_extvalues_len, void* ctx); /* plonky2_gpu.cu:192-215 */
+/* plonky2_gpu.cu:88-136 (defined by the reference, not declared in lib.rs): coset LDE of the coefficient columns into the
+ * work area as a column-major [poly_num][N] matrix in natural point order. */
+p2b_rust_error fft_blinding(uint64_t* d_values_flatten, uint64_t* d_ext_values_flatten, int poly_num, int values_num_per_poly,
+                            int log_len, const uint64_t* d_root_table2, const uint64_t* d_shift_powers, int rate_bits,
+                            int pad_extvalues_len, void* ctx);
 /* lib.rs:117-143.  The reference kernel is compiled for ONE circuit; this one evaluates the circuit registered with
  * p2b_compat_set_circuit().  d_outs: [N][num_challenges] values, d_quotient_polys: [num_challenges][N] coefficients. */
 p2b_rust_error compute_quotient_polys(const uint64_t* d_ext_values_flatten, int poly_num, int values_num_per_poly, int log_len,

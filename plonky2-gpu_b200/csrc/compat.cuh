@@ -29,29 +29,42 @@ static p2b_rust_error rust_err(int rc) {
                         m && *m ? strdup(m) : nullptr};
 }
 
-// one lazily created context per device for the legacy entry points; its main stream is replaced by the
-// caller's stream for the duration of a call (the reference launches everything on ctx->stream).
-static int compat_ctx(void* ref_ctx, p2b_ctx** out, cudaStream_t* saved) {
-  int dev = 0;
-  CUDA_TRY(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64) return fail(P2B_ERR_INVALID, "device index %d", dev);
-  std::lock_guard<std::mutex> lk(g_compat_mu);
-  if (!g_compat_ctx[dev]) P2B_TRY(p2b_ctx_create(dev, &g_compat_ctx[dev]));
-  p2b_ctx* c = g_compat_ctx[dev];
-  *saved = c->stream;
-  if (ref_ctx) {
-    cudaStream_t s = static_cast<RefStreams*>(ref_ctx)->stream;
-    if (s) c->stream = s;
+// One lazily created context per device for the legacy entry points.  A legacy call holds g_compat_mu from entry to
+// return (CompatCall): the shared context's main stream is replaced by the caller's stream for the duration of the call
+// (the reference launches everything on ctx->stream), and its scratch buffer and events are not reentrant, so two host
+// threads calling the legacy symbols are serialised instead of corrupting each other (the reference's own caller is
+// single-threaded per CudaInvContext, plonky2/src/fri/oracle.rs:279-545).
+struct CompatCall {
+  std::unique_lock<std::mutex> lk;
+  p2b_ctx* c = nullptr;
+  cudaStream_t saved = nullptr;
+  int rc = P2B_OK;
+  explicit CompatCall(void* ref_ctx) : lk(g_compat_mu) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { rc = fail(P2B_ERR_CUDA, "cudaGetDevice failed"); return; }
+    if (dev < 0 || dev >= 64) { rc = fail(P2B_ERR_INVALID, "device index %d", dev); return; }
+    if (!g_compat_ctx[dev]) {
+      rc = p2b_ctx_create(dev, &g_compat_ctx[dev]);
+      if (rc != P2B_OK) return;
+    }
+    c = g_compat_ctx[dev];
+    saved = c->stream;
+    if (ref_ctx) {
+      cudaStream_t s = static_cast<RefStreams*>(ref_ctx)->stream;
+      if (s) c->stream = s;
+    }
   }
-  *out = c;
-  return P2B_OK;
-}
+  ~CompatCall() {
+    if (c) c->stream = saved;
+  }
+  // wait for the caller's stream (the reference synchronises after every kernel) and translate the status
+  p2b_rust_error finish(int status) {
+    if (status == P2B_OK && c && cudaStreamSynchronize(c->stream) != cudaSuccess) status = fail(P2B_ERR_CUDA, "stream synchronize failed");
+    return status == P2B_OK ? rust_ok() : rust_err(status);
+  }
+};
 
-extern "C" void init(void) {
-  p2b_ctx* c;
-  cudaStream_t saved;
-  if (compat_ctx(nullptr, &c, &saved) == P2B_OK) c->stream = saved;
-}
+extern "C" void init(void) { CompatCall call(nullptr); }
 
 // ifft: in-place inverse NTT of poly_num columns (cuda/plonky2_gpu.cu:70-86; oracle.rs:394-401)
 extern "C" p2b_rust_error ifft(uint64_t* d_values_flatten, int poly_num, int values_num_per_poly, int log_len,
@@ -62,22 +75,21 @@ extern "C" p2b_rust_error ifft(uint64_t* d_values_flatten, int poly_num, int val
     fail(P2B_ERR_INVALID, "ifft: bad arguments");
     return rust_err(P2B_ERR_INVALID);
   }
-  p2b_ctx* c;
-  cudaStream_t saved;
-  int rc = compat_ctx(ctx, &c, &saved);
-  if (rc != P2B_OK) return rust_err(rc);
-  rc = p2b_ifft_batch(c, d_values_flatten, d_values_flatten, (u32)log_len, (u64)poly_num);
-  if (rc == P2B_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(P2B_ERR_CUDA, "ifft: stream synchronize failed");
-  c->stream = saved;
-  return rc == P2B_OK ? rust_ok() : rust_err(rc);
+  CompatCall call(ctx);
+  if (call.rc != P2B_OK) return rust_err(call.rc);
+  return call.finish(p2b_ifft_batch(call.c, d_values_flatten, d_values_flatten, (u32)log_len, (u64)poly_num));
 }
 
 static int compat_from_coeffs(p2b_ctx* c, RefStreams* rs, u64* base, int poly_num, int log_len, int rate_bits,
                               int salt_size, int cap_height, long long pad) {
-  if (salt_size != 0)
-    return fail(P2B_ERR_UNSUPPORTED, "legacy entry points do not carry blinding columns; use p2b_commit_* with a salt");
+  // Blinding (salt_size = SALT_SIZE = 4, oracle.rs:302): the reference never uploads salt values -- its hash_leaves /
+  // transpose kernels read columns [poly_num, poly_num + salt_size) of the column-major work area as they find them
+  // (plonky2_gpu.cu:552-600: those columns are neither written by the LDE nor bit-reversed), i.e. leaf L gets
+  // work[(poly_num + s) * N + L].  The same words are used here (canonicalised), so a caller that fills them gets
+  // exactly its salt and one that does not gets the same "whatever the device buffer held" the reference hashes.
+  if (salt_size < 0 || salt_size > 64) return fail(P2B_ERR_INVALID, "salt_size %d", salt_size);
   const u64 P = (u64)poly_num, n = (u64)1 << log_len, N = n << rate_bits;
-  if ((u64)pad < N * P) return fail(P2B_ERR_INVALID, "pad_extvalues_len smaller than the LDE matrix");
+  if ((u64)pad < N * (P + (u64)salt_size)) return fail(P2B_ERR_INVALID, "pad_extvalues_len smaller than the LDE matrix");
   const u64 ncap = (u64)1 << cap_height;
   u64* work = base + pad;
   u64* digests = work + N * (P + (u64)salt_size);  // d_digest_buf, plonky2_gpu.cu:552
@@ -90,8 +102,9 @@ static int compat_from_coeffs(p2b_ctx* c, RefStreams* rs, u64* base, int poly_nu
   }
   // intermediates live in the work area; coset blocks are produced in descending order so that block 0,
   // whose rows overwrite the coefficients, is written last and only after stream2's copy has finished.
-  return lde_and_merkle(c, coeffs, (u32)log_len, P, (u32)rate_bits, (u32)cap_height, nullptr, work, base, P, digests, cap,
-                        true, rs ? rs->stream2 : nullptr, 0, (u64)1 << rate_bits, nullptr);
+  return lde_and_merkle(c, coeffs, (u32)log_len, P, (u32)rate_bits, (u32)cap_height, nullptr, work, base, P + (u64)salt_size, digests, cap,
+                        true, rs ? rs->stream2 : nullptr, 0, (u64)1 << rate_bits, nullptr, salt_size ? work + P * N : nullptr,
+                        (u32)salt_size);
 }
 
 // merkle_tree_from_coeffs (cuda/plonky2_gpu.cu:435-606; oracle.rs:409-422, 599-627)
@@ -108,15 +121,10 @@ extern "C" p2b_rust_error merkle_tree_from_coeffs(uint64_t* d_values_flatten, ui
     fail(P2B_ERR_INVALID, "merkle_tree_from_coeffs: bad arguments (the reference passes the same pointer for values and ext_values)");
     return rust_err(P2B_ERR_INVALID);
   }
-  p2b_ctx* c;
-  cudaStream_t saved;
-  int rc = compat_ctx(ctx, &c, &saved);
-  if (rc != P2B_OK) return rust_err(rc);
-  rc = compat_from_coeffs(c, static_cast<RefStreams*>(ctx), d_values_flatten, poly_num, log_len, rate_bits, salt_size, cap_height,
-                          pad_extvalues_len);
-  if (rc == P2B_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(P2B_ERR_CUDA, "stream synchronize failed");
-  c->stream = saved;
-  return rc == P2B_OK ? rust_ok() : rust_err(rc);
+  CompatCall call(ctx);
+  if (call.rc != P2B_OK) return rust_err(call.rc);
+  return call.finish(compat_from_coeffs(call.c, static_cast<RefStreams*>(ctx), d_values_flatten, poly_num, log_len, rate_bits, salt_size,
+                                        cap_height, pad_extvalues_len));
 }
 
 // merkle_tree_from_values (declared lib.rs:83-98; the reference's body is `assert(0)`, plonky2_gpu.cu:228):
@@ -155,10 +163,10 @@ extern "C" p2b_rust_error build_merkle_tree(uint64_t* d_ext_values_flatten, int 
     fail(P2B_ERR_INVALID, "build_merkle_tree: bad arguments");
     return rust_err(P2B_ERR_INVALID);
   }
-  p2b_ctx* c;
-  cudaStream_t saved;
-  int rc = compat_ctx(ctx, &c, &saved);
-  if (rc != P2B_OK) return rust_err(rc);
+  CompatCall call(ctx);
+  if (call.rc != P2B_OK) return rust_err(call.rc);
+  p2b_ctx* c = call.c;
+  int rc = P2B_OK;
   const u64 N = (u64)values_num_per_poly << rate_bits, cols = (u64)poly_num + salt_size;
   const u32 log_N = (u32)(log_len + rate_bits);
   u64* m = d_ext_values_flatten + pad_extvalues_len;
@@ -169,9 +177,7 @@ extern "C" p2b_rust_error build_merkle_tree(uint64_t* d_ext_values_flatten, int 
   c->launches++;
   if (cudaGetLastError() != cudaSuccess) rc = fail(P2B_ERR_CUDA, "bit-reversal launch failed");
   if (rc == P2B_OK) rc = p2b_merkle_tree(c, m, N, cols, 1, N, (u32)cap_height, digests, cap);
-  if (rc == P2B_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(P2B_ERR_CUDA, "stream synchronize failed");
-  c->stream = saved;
-  return rc == P2B_OK ? rust_ok() : rust_err(rc);
+  return call.finish(rc);
 }
 
 // transpose (plonky2_gpu.cu:192-215): column-major [cols][N] in the work area -> row-major [N][cols] at base.
@@ -194,18 +200,60 @@ extern "C" p2b_rust_error transpose(uint64_t* d_ext_values_flatten, int poly_num
     fail(P2B_ERR_INVALID, "transpose: bad arguments");
     return rust_err(P2B_ERR_INVALID);
   }
-  p2b_ctx* c;
-  cudaStream_t saved;
-  int rc = compat_ctx(ctx, &c, &saved);
-  if (rc != P2B_OK) return rust_err(rc);
+  CompatCall call(ctx);
+  if (call.rc != P2B_OK) return rust_err(call.rc);
+  p2b_ctx* c = call.c;
+  int rc = P2B_OK;
   const u64 N = (u64)values_num_per_poly << rate_bits, cols = (u64)poly_num + salt_size;
   dim3 grid((unsigned)((N + 31) / 32), (unsigned)((cols + 31) / 32)), block(32, 8);
   transpose_to_rows_kernel<<<grid, block, 0, c->stream>>>(d_ext_values_flatten + pad_extvalues_len, d_ext_values_flatten, N, cols);
   c->launches++;
   if (cudaGetLastError() != cudaSuccess) rc = fail(P2B_ERR_CUDA, "transpose launch failed");
-  if (rc == P2B_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(P2B_ERR_CUDA, "stream synchronize failed");
-  c->stream = saved;
-  return rc == P2B_OK ? rust_ok() : rust_err(rc);
+  return call.finish(rc);
+}
+
+// fft_blinding (plonky2_gpu.cu:88-136; defined by the reference but not declared in lib.rs): coset LDE of the coefficient
+// columns at base[0 .. n*P) into the work area base[pad ..] as a column-major [P][N] matrix in NATURAL point order (no
+// bit reversal, no transpose, no hashing -- the caller follows it with build_merkle_tree + transpose).
+__global__ void leaves_to_colmajor_natural_kernel(const u64* __restrict__ leaves, u64* __restrict__ dst, u64 N, u32 log_N, u64 cols) {
+  __shared__ u64 tile[32][33];
+  u64 r0 = (u64)blockIdx.x * 32, c0 = (u64)blockIdx.y * 32;  // r = natural point index
+  for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+    u64 r = r0 + k, c = c0 + threadIdx.x;
+    if (c < cols && r < N) tile[k][threadIdx.x] = leaves[(log_N ? (__brevll(r) >> (64 - log_N)) : 0) * cols + c];
+  }
+  __syncthreads();
+  for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+    u64 c = c0 + k, r = r0 + threadIdx.x;
+    if (c < cols && r < N) dst[c * N + r] = tile[threadIdx.x][k];
+  }
+}
+extern "C" p2b_rust_error fft_blinding(uint64_t* d_values_flatten, uint64_t* d_ext_values_flatten, int poly_num, int values_num_per_poly,
+                                       int log_len, const uint64_t* d_root_table2, const uint64_t* d_shift_powers, int rate_bits,
+                                       int pad_extvalues_len, void* ctx) {
+  (void)d_root_table2;
+  (void)d_shift_powers;
+  if (!d_values_flatten || !d_ext_values_flatten || poly_num <= 0 || log_len < 0 || values_num_per_poly != (1 << log_len) || rate_bits < 0) {
+    fail(P2B_ERR_INVALID, "fft_blinding: bad arguments");
+    return rust_err(P2B_ERR_INVALID);
+  }
+  CompatCall call(ctx);
+  if (call.rc != P2B_OK) return rust_err(call.rc);
+  p2b_ctx* c = call.c;
+  const u64 P = (u64)poly_num, N = (u64)values_num_per_poly << rate_bits;
+  const u32 log_N = (u32)(log_len + rate_bits);
+  u64* rows = nullptr;
+  int rc = P2B_OK;
+  if (cudaMallocAsync(&rows, N * P * sizeof(u64), c->stream) != cudaSuccess) rc = fail(P2B_ERR_OOM, "fft_blinding: scratch allocation failed");
+  if (rc == P2B_OK) rc = p2b_lde_leaves(c, d_values_flatten, (u32)log_len, P, (u32)rate_bits, rows, P, 0);
+  if (rc == P2B_OK) {
+    dim3 grid((unsigned)((N + 31) / 32), (unsigned)((P + 31) / 32)), block(32, 8);
+    leaves_to_colmajor_natural_kernel<<<grid, block, 0, c->stream>>>(rows, d_ext_values_flatten + pad_extvalues_len, N, log_N, P);
+    c->launches++;
+    if (cudaGetLastError() != cudaSuccess) rc = fail(P2B_ERR_CUDA, "fft_blinding: launch failed");
+  }
+  if (rows) cudaFreeAsync(rows, c->stream);
+  return call.finish(rc);
 }
 
 // compute_quotient_polys (lib.rs:117-143; plonky2_gpu.cu:609-783).  The reference's kernel is compiled for one circuit
@@ -250,6 +298,8 @@ extern "C" p2b_rust_error compute_quotient_polys(const uint64_t* d_ext_values_fl
                                                  const p2b_data_slice* alphas, const p2b_data_slice* betas,
                                                  const p2b_data_slice* gammas, void* ctx) {
   (void)d_root_table2; (void)d_shift_inv_powers; (void)points; (void)z_h_on_coset_evals; (void)z_h_on_coset_inverses; (void)k_is;
+  CompatCall call(ctx);   // also guards g_compat_circuit against a concurrent p2b_compat_set_circuit
+  if (call.rc != P2B_OK) return rust_err(call.rc);
   CompatCircuit& cc = g_compat_circuit;
   if (!cc.set) {
     fail(P2B_ERR_INVALID, "compute_quotient_polys: no circuit registered; call p2b_compat_set_circuit() first (the reference kernel "
@@ -269,10 +319,8 @@ extern "C" p2b_rust_error compute_quotient_polys(const uint64_t* d_ext_values_fl
     fail(P2B_ERR_INVALID, "compute_quotient_polys: leaf slices are not a multiple of the LDE size");
     return rust_err(P2B_ERR_INVALID);
   }
-  p2b_ctx* c;
-  cudaStream_t saved;
-  int rc = compat_ctx(ctx, &c, &saved);
-  if (rc != P2B_OK) return rust_err(rc);
+  p2b_ctx* c = call.c;
+  int rc = P2B_OK;
   u64 h[3][quotient::MAX_CHALLENGES];
   const p2b_data_slice* sl[3] = {alphas, betas, gammas};
   for (int k = 0; k < 3 && rc == P2B_OK; k++)
@@ -283,7 +331,5 @@ extern "C" p2b_rust_error compute_quotient_polys(const uint64_t* d_ext_values_fl
     rc = quotient_impl(c, &circ, d_ext_values_flatten, (u64)poly_num + salt_size, (const u64*)zs_pp_leaves->ptr,
                        (u64)zs_pp_leaves->len / N, (const u64*)consts_sigmas_leaves->ptr, (u64)consts_sigmas_leaves->len / N, cc.pih,
                        h[1], h[2], h[0], nullptr, (u64*)d_quotient_polys, (u64*)d_outs);
-  if (rc == P2B_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(P2B_ERR_CUDA, "stream synchronize failed");
-  c->stream = saved;
-  return rc == P2B_OK ? rust_ok() : rust_err(rc);
+  return call.finish(rc);
 }

@@ -227,8 +227,8 @@ extern "C" int p2b_ctx_create(int device, p2b_ctx** out) {
 extern "C" void p2b_ctx_destroy(p2b_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  if (c->stream) cudaStreamSynchronize(c->stream);
-  if (c->stream2) cudaStreamSynchronize(c->stream2);
+  for (cudaStream_t st : {c->stream, c->stream2, c->stream_h2d, c->stream_d2h})   // all four: copies may still be in flight
+    if (st) cudaStreamSynchronize(st);
   cudaFree(c->U_fwd);
   cudaFree(c->U_inv);
   cudaFree(c->d_roots);
@@ -503,6 +503,14 @@ __global__ void scatter_salt_kernel(const u64* __restrict__ salt, u64 N, u32 log
   for (int cidx = 0; cidx < P2B_SALT_SIZE; cidx++) leaves[i * row_stride + col0 + cidx] = gl::canon(salt[(u64)cidx * N + src]);
 }
 
+// leaf row leaf0 + i, column col0 + c  <-  salt[c][leaf0 + i]   (the reference's device layout, compat.cuh)
+__global__ void gather_salt_by_leaf_kernel(const u64* __restrict__ salt, u64 N, u64 leaf0, u64 count, u32 ncols,
+                                           u64* __restrict__ rows, u64 row_stride, u64 col0) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  for (u32 cidx = 0; cidx < ncols; cidx++) rows[i * row_stride + col0 + cidx] = gl::canon(salt[(u64)cidx * N + leaf0 + i]);
+}
+
 // ======================================================================================================
 // batch
 // ======================================================================================================
@@ -541,7 +549,9 @@ extern "C" void p2b_batch_destroy(p2b_batch* b) { batch_free(b); }
 static int lde_and_merkle(p2b_ctx* c, const u64* coeffs_d, u32 k, u64 P, u32 rate_bits, u32 cap_height,
                           const u64* salt_d, u64* tmp, u64* leaves_d, u64 leaf_len, u64* digests_d, u64* cap_d,
                           bool descending, cudaStream_t wait_before_block0, u64 block_first, u64 block_count,
-                          u32* top_layer) {
+                          u32* top_layer, const u64* salt_by_leaf = nullptr, u32 salt_by_leaf_cols = 0) {
+  // salt_by_leaf (reference device layout, compat.cuh): column-major [salt cols][N] indexed by LEAF; gathered per coset
+  // block after that block's rows are written (the rows of block 0 may alias the coefficients, which must be consumed first)
   // leaves_d row 0 is global leaf block_first * n (a shard holds only its own coset blocks' rows)
   const u64 n = (u64)1 << k, N = n << rate_bits;
   const u32 log_N = k + rate_bits;
@@ -561,6 +571,12 @@ static int lde_and_merkle(p2b_ctx* c, const u64* coeffs_d, u32 k, u64 P, u32 rat
     u64 b = block_first + (descending ? block_count - 1 - i : i);
     if (b == 0 && wait_before_block0) CUDA_TRY(cudaStreamSynchronize(wait_before_block0));
     P2B_TRY(run_lde_block(c, c->stream, coeffs_d, n, tmp, k, P, b, sc, leaves_d, leaf_len, 0, (b - block_first) * n));
+    if (salt_by_leaf) {
+      gather_salt_by_leaf_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(salt_by_leaf, N, b * n, n, salt_by_leaf_cols,
+                                                                                    leaves_d + (b - block_first) * n * leaf_len, leaf_len, P);
+      c->launches++;
+      CUDA_TRY(cudaGetLastError());
+    }
     // hash this block's rows on stream2 while the next block's NTT runs on stream
     CUDA_TRY(cudaEventRecord(c->ev_a, c->stream));
     CUDA_TRY(cudaStreamWaitEvent(c->stream2, c->ev_a, 0));
