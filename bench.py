@@ -240,19 +240,14 @@ def parity_preflight(p2b, sharded, ctx, engine, comm, commit_sharded, rank, worl
             raise SystemExit("bench.py: parity preflight failed (2^%d x %d commit differs from the CPU oracle)" % (n_log, P))
         return "2^%d x %d: coefficients, leaves, digests, cap == CPU oracle" % (n_log, P)
     if pipelined:
-        rounds, my_blocks = sharded.cyclic_column_blocks(P, world, rank)
-        shard = np.zeros((rounds * 8, n), dtype=np.uint64)
-        for j, q in enumerate(my_blocks):
-            if q is not None:
-                c0, c1 = 8 * q, min(8 * q + 8, P)
-                shard[8 * j: 8 * j + (c1 - c0)] = values[c0:c1]
+        shard = sharded.pack_local(values, P, world, rank)
     else:
         c0, c1, cmax = sharded.column_shard(P, world, rank)
         shard = np.zeros((cmax, n), dtype=np.uint64)
         shard[: c1 - c0] = values[c0:c1]
     t = torch.from_numpy(shard.view(np.int64)).cuda()
     b = commit_sharded(engine, comm, t, P, n_log, RATE_BITS, CAP_HEIGHT)
-    ctx.synchronize()
+    engine.synchronize()
     per = N // world
     ok = np.array_equal(b.cap(), want.cap)
     mine = b.leaves()
@@ -288,13 +283,13 @@ def run_b200(args, rank, world, local_rank):
     n_log, P = args.n_log, args.polys
     n, N = 1 << n_log, 1 << (n_log + RATE_BITS)
     # ---- inputs resident in HBM: this rank's columns of the synthetic value matrix ----
-    # N = 1: all P columns.  N > 1: the rank's 8-column blocks of the pipelined flow (sharded.cyclic_column_blocks: block q =
-    # columns [8q, 8q + 8) belongs to rank q % N), rows [8j, 8j + 8) = its block of exchange round j, zero rows where absent.
+    # N = 1: all P columns.  N > 1: the rank's slice of every exchange round of the pipelined flow (sharded.local_layout:
+    # round j = consecutive columns [col0_j, col0_j + width_j), of which rank r holds `per_j` consecutive ones at rows
+    # [row0_j, row0_j + per_j) of its local buffer; zero rows where a round is ragged).
     pipelined = world > 1 and P > 4 and not os.environ.get("P2B_BENCH_UNPIPELINED")  # env knob: A/B against the one-shot exchange
     if pipelined:
-        rounds, my_blocks = sharded.cyclic_column_blocks(P, world, rank)
-        cmax = rounds * 8
-        col_ranges = [(8 * j, 8 * q, min(8 * q + 8, P)) for j, q in enumerate(my_blocks) if q is not None]   # (local row, c0, c1)
+        cmax, layout = sharded.local_layout(P, world, rank)
+        col_ranges = [(row0, a_, b_) for row0, a_, b_ in layout if b_ > a_]   # (local row, c0, c1)
     else:
         c0, c1, cmax = sharded.column_shard(P, world, rank)
         col_ranges = [(0, c0, c1)] if c1 > c0 else []
@@ -323,7 +318,7 @@ def run_b200(args, rank, world, local_rank):
         else:
             work.copy_(vals)  # the sharded path transforms its columns in place
             b = commit_sharded(engine, comm, work, P, n_log, RATE_BITS, CAP_HEIGHT)
-        ctx.synchronize()
+        engine.synchronize()
         return b
 
     class _Ptr:  # minimal DeviceBuffer stand-in for torch-owned memory
@@ -401,6 +396,7 @@ def run_b200(args, rank, world, local_rank):
             def coeffs_to_host(shard):
                 # each rank returns the coefficient columns it transformed, on a side stream while the exchange, the LDE
                 # and the tree run (the single-GPU call does the same inside p2b_commit_from_values_ex)
+                copy_stream.wait_stream(torch.cuda.current_stream())   # the engine ordered the transforms before this stream
                 with torch.cuda.stream(copy_stream):
                     for row, a_, b_ in col_ranges:
                         host_coef_t[row * n: (row + b_ - a_) * n].copy_(shard.view(-1)[row * n: (row + b_ - a_) * n], non_blocking=True)
@@ -409,7 +405,7 @@ def run_b200(args, rank, world, local_rank):
             b.cap(out=cap_host)
             copy_stream.synchronize()
             b.close()
-        ctx.synchronize()
+        engine.synchronize()
 
     for _ in range(2):
         step_e2e()
@@ -484,8 +480,8 @@ def run_b200(args, rank, world, local_rank):
             "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": workload_name(n_log, P),
-                       "sharding": ("8-column blocks dealt round-robin for the iNTT, one NCCL all-gather per round overlapped with LDE + progressive leaf "
-                                    "hashing of the previous round, coset blocks / cap sub-trees per rank") if pipelined
+                       "sharding": ("columns dealt in exchange rounds of 8, 8, 16, .. 8N consecutive columns for the iNTT, one NCCL all-gather per round "
+                                    "overlapped with LDE + progressive leaf hashing of the previous round, coset blocks / cap sub-trees per rank") if pipelined
                        else ("columns for iNTT, coset blocks / cap sub-trees for LDE+Merkle" if world > 1 else "single GPU"),
                        "l2": "inputs_exceed_l2 (values %.2f GB, LDE %.2f GB per step vs 126 MB L2)" % (P * n * 8 / 1e9, P * N * 8 / 1e9),
                        "timing": "CUDA events on the library stream around all steps, max over ranks; wall %.1f ms/step" % (wall_ms / args.steps),
@@ -516,8 +512,11 @@ def run_b200(args, rank, world, local_rank):
             ms, cores = cpu_commit_ms(sample_log, P, reps=2)
             line["cpu_baseline"] = cpu_baseline_obj(args, ms * (1 << (n_log - sample_log)), cores, sample_log)
         print(json.dumps(line), flush=True)
+    engine.synchronize()
+    torch.cuda.synchronize()
     host_vals.free()
     host_coef.free()
+    del engine
     ctx.close()
     if world > 1:
         dist.barrier()

@@ -159,6 +159,45 @@ int p2b_batch_import_nodes(p2b_batch* b, uint32_t layer, uint64_t node_first, ui
 int p2b_batch_finish_layers(p2b_batch* b, uint32_t from_layer);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Single-process multi-device commit (SURVEY.md sections 5 / 8b: "one process, 8 devices").  The reference's caller is
+ * ONE prover process (plonky2/src/fri/oracle.rs:279-545 from_values_with_gpu, plonk/prover.rs:239-700 my_prove), so this
+ * is the entry a Rust prover binds to use every GPU of a node: `devices` are CUDA ordinals (NULL = 0..n-1), n a power of
+ * two <= 2^rate_bits.  The value columns are dealt over the devices in growing exchange rounds, inverse-transformed
+ * where they land, pushed to every peer over NVLink (cudaMemcpyPeerAsync, ordered by cross-device events -- there is no
+ * host synchronisation inside a commit) and absorbed round by round by the leaves of the coset blocks each device owns;
+ * the cap entries are exchanged at the end.  Results are bit-identical to p2b_commit_from_values.  INTEGRATION.md shows
+ * the Rust call.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct p2b_mgpu p2b_mgpu;
+typedef struct p2b_mgpu_batch p2b_mgpu_batch;
+int p2b_mgpu_create(const int* devices, int n_dev, p2b_mgpu** out);
+void p2b_mgpu_destroy(p2b_mgpu* g);
+int p2b_mgpu_device_count(const p2b_mgpu* g);
+p2b_ctx* p2b_mgpu_ctx(p2b_mgpu* g, int index);   /* the per-device context (quotient / FRI calls on that device's shard) */
+int p2b_mgpu_peer_access(const p2b_mgpu* g);     /* 1 if every pair of devices has direct peer access */
+int p2b_mgpu_synchronize(p2b_mgpu* g);
+int p2b_mgpu_timer_start(p2b_mgpu* g);           /* CUDA events on every device's stream ... */
+int p2b_mgpu_timer_stop_ms(p2b_mgpu* g, float* ms_max); /* ... longest span over the devices */
+/* PolynomialBatch::from_values (fri/oracle.rs:709-731): values_host [P][n] column-major (pinned memory overlaps the upload with
+ * the transforms; it must stay valid until p2b_mgpu_synchronize); coeffs_host_out NULL or [P][n] (valid after the same). */
+int p2b_mgpu_commit_from_values(p2b_mgpu* g, const uint64_t* values_host, uint32_t degree_log, uint64_t num_polys,
+                                uint32_t rate_bits, uint32_t cap_height, uint64_t* coeffs_host_out, p2b_mgpu_batch** out);
+/* Inputs already resident on the devices.  The columns are dealt in exchange rounds of 8, 8, 16, 32, .. 8*n_dev consecutive
+ * columns (p2b_mgpu_round); device `index` holds, for round j, its `per` columns [col0 + index*per, ...) at rows
+ * [row0, row0 + per) of its local buffer [sum of per][n] (zero rows where a round is ragged).  The commit transforms them in place. */
+int p2b_mgpu_resident_cols(p2b_mgpu* g, int index, uint32_t degree_log, uint64_t num_polys, uint64_t** d_cols_out, uint64_t* rounds_out);
+int p2b_mgpu_round(const p2b_mgpu* g, uint64_t num_polys, uint64_t j, uint64_t* col0, uint64_t* width, uint64_t* per, uint64_t* row0);
+int p2b_mgpu_commit_resident(p2b_mgpu* g, uint32_t degree_log, uint64_t num_polys, uint32_t rate_bits, uint32_t cap_height,
+                             uint64_t* coeffs_host_out, p2b_mgpu_batch** out);
+void p2b_mgpu_batch_destroy(p2b_mgpu_batch* b);
+int p2b_mgpu_batch_get_info(const p2b_mgpu_batch* b, p2b_batch_info* out);
+p2b_batch* p2b_mgpu_batch_shard(p2b_mgpu_batch* b, int index);  /* device `index`'s leaves [index*N/n_dev, (index+1)*N/n_dev) */
+int p2b_mgpu_batch_get_cap(const p2b_mgpu_batch* b, uint64_t* out /* [2^cap_height][4] */);
+int p2b_mgpu_batch_open_rows(const p2b_mgpu_batch* b, const uint64_t* leaf_indices, uint64_t count, uint64_t* rows_out,
+                             uint64_t* siblings_out /* or NULL */);
+int p2b_mgpu_batch_get_leaves(const p2b_mgpu_batch* b, uint64_t first_leaf, uint64_t count, uint64_t* out);
+
+/* ---------------------------------------------------------------------------------------------------
  * Quotient polynomials: compute_quotient_polys (plonky2/src/plonk/prover.rs:790-1034) for a circuit given as data.
  * The reference CUDA kernel hard-codes one circuit (cuda/plonky2_gpu_impl.cuh:600-685, plonky2_gpu.cu:665-689); here
  * the host passes the part of CommonCircuitData the evaluation reads (circuit_data.rs:270-349).

@@ -196,6 +196,26 @@ def lib():
         "p2b_memcpy_d2h": (i, [vp, vp, vp, u64]),
         "p2b_timer_start": (i, [vp]),
         "p2b_timer_stop_ms": (i, [vp, C.POINTER(C.c_float)]),
+        # single-process multi-device commit
+        "p2b_mgpu_create": (i, [C.POINTER(C.c_int), i, C.POINTER(vp)]),
+        "p2b_mgpu_destroy": (None, [vp]),
+        "p2b_mgpu_device_count": (i, [vp]),
+        "p2b_mgpu_ctx": (vp, [vp, i]),
+        "p2b_mgpu_peer_access": (i, [vp]),
+        "p2b_mgpu_synchronize": (i, [vp]),
+        "p2b_mgpu_timer_start": (i, [vp]),
+        "p2b_mgpu_timer_stop_ms": (i, [vp, C.POINTER(C.c_float)]),
+        "p2b_mgpu_commit_from_values": (i, [vp, vp, u32, u64, u32, u32, vp, C.POINTER(vp)]),
+        "p2b_mgpu_resident_cols": (i, [vp, i, u32, u64, C.POINTER(vp), C.POINTER(u64)]),
+        "p2b_mgpu_commit_resident": (i, [vp, u32, u64, u32, u32, vp, C.POINTER(vp)]),
+        "p2b_mgpu_round": (i, [vp, u64, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]),
+        "p2b_mgpu_batch_destroy": (None, [vp]),
+        "p2b_mgpu_batch_get_info": (i, [vp, C.POINTER(BatchInfo)]),
+        "p2b_mgpu_batch_shard": (vp, [vp, i]),
+        "p2b_mgpu_batch_get_cap": (i, [vp, vp]),
+        "p2b_mgpu_batch_open_rows": (i, [vp, vp, u64, vp, vp]),
+        "p2b_mgpu_batch_get_leaves": (i, [vp, u64, u64, vp]),
+        "fft_blinding": (RustError, [vp, vp, i, i, i, vp, vp, i, i, vp]),
         # reference-compatible symbols (cuda/src/lib.rs:52-145)
         "init": (None, []),
         "ifft": (RustError, [vp, i, i, i, vp, vp, vp]),
@@ -666,4 +686,102 @@ class PolynomialBatch:
         sib = np.empty((idx.size, layers, 4), dtype=np.uint64) if with_proofs else None
         _check(lib().p2b_batch_open_rows(self.handle, idx.ctypes.data, idx.size, rows.ctypes.data,
                                          sib.ctypes.data if (with_proofs and layers) else None))
+        return rows, sib
+
+
+class MultiGpu:
+    """p2b_mgpu: ONE process driving several devices (the shape of the reference's caller, fri/oracle.rs:279-545)."""
+
+    def __init__(self, devices=None, count=None):
+        if devices is None:
+            devices = list(range(count if count is not None else 1))
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        _check(lib().p2b_mgpu_create(arr, len(devices), C.byref(h)))
+        self.handle, self.devices = h, list(devices)
+
+    def close(self):
+        if self.handle:
+            lib().p2b_mgpu_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def peer_access(self):
+        return bool(lib().p2b_mgpu_peer_access(self.handle))
+
+    def synchronize(self):
+        _check(lib().p2b_mgpu_synchronize(self.handle))
+
+    def timer_start(self):
+        _check(lib().p2b_mgpu_timer_start(self.handle))
+
+    def timer_stop_ms(self):
+        ms = C.c_float()
+        _check(lib().p2b_mgpu_timer_stop_ms(self.handle, C.byref(ms)))
+        return ms.value
+
+    def commit_from_values(self, values, rate_bits, cap_height, coeffs_out=None):
+        """values: host array [P][n] (numpy; pinned memory via PinnedBuffer overlaps the upload)."""
+        v = values if (isinstance(values, np.ndarray) and values.dtype == np.uint64 and values.flags.c_contiguous) else _np(values)
+        P, n = v.shape
+        h = C.c_void_p()
+        _check(lib().p2b_mgpu_commit_from_values(self.handle, v.ctypes.data, n.bit_length() - 1, P, rate_bits, cap_height,
+                                                 coeffs_out.ctypes.data if coeffs_out is not None else None, C.byref(h)))
+        b = MultiGpuBatch(self, h)
+        b._keep = (v, coeffs_out)
+        return b
+
+    def resident_cols(self, index, degree_log, num_polys):
+        ptr, rounds = C.c_void_p(), C.c_uint64()
+        _check(lib().p2b_mgpu_resident_cols(self.handle, index, degree_log, num_polys, C.byref(ptr), C.byref(rounds)))
+        return ptr.value, rounds.value
+
+    def commit_resident(self, degree_log, num_polys, rate_bits, cap_height):
+        h = C.c_void_p()
+        _check(lib().p2b_mgpu_commit_resident(self.handle, degree_log, num_polys, rate_bits, cap_height, None, C.byref(h)))
+        return MultiGpuBatch(self, h)
+
+
+class MultiGpuBatch:
+    def __init__(self, mg, handle):
+        self.mg, self.handle = mg, handle
+        info = BatchInfo()
+        _check(lib().p2b_mgpu_batch_get_info(handle, C.byref(info)))
+        self.info = info
+        self.leaf_len, self.num_leaves, self.cap_height = info.leaf_len, info.num_leaves, info.cap_height
+        self.layers = info.degree_log + info.rate_bits - info.cap_height
+
+    def close(self):
+        if self.handle:
+            lib().p2b_mgpu_batch_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def cap(self):
+        out = np.empty((1 << self.cap_height, 4), dtype=np.uint64)
+        _check(lib().p2b_mgpu_batch_get_cap(self.handle, out.ctypes.data))
+        return out
+
+    def leaves(self, first=0, count=None):
+        count = self.num_leaves - first if count is None else count
+        out = np.empty((count, self.leaf_len), dtype=np.uint64)
+        _check(lib().p2b_mgpu_batch_get_leaves(self.handle, first, count, out.ctypes.data))
+        return out
+
+    def open_rows(self, leaf_indices):
+        idx = _np(leaf_indices)
+        rows = np.empty((idx.size, self.leaf_len), dtype=np.uint64)
+        sib = np.empty((idx.size, self.layers, 4), dtype=np.uint64)
+        _check(lib().p2b_mgpu_batch_open_rows(self.handle, idx.ctypes.data, idx.size, rows.ctypes.data, sib.ctypes.data if self.layers else None))
         return rows, sib

@@ -1,0 +1,474 @@
+// mgpu.cuh -- single-process, multi-device commit: the shape the reference's caller has (ONE prover process,
+// plonky2/src/fri/oracle.rs:279-545 `from_values_with_gpu`, plonky2/src/plonk/prover.rs:239-700 `my_prove`), so a Rust
+// prover can drive all GPUs of a node through the C ABI.  Included at the end of plonky2_b200.cu (single translation unit).
+//
+// Partition (the same as plonky2-gpu_b200/sharded.py, which drives one process per GPU for bench.py):
+//   * the value matrix is dealt in exchange rounds of 8, 8, 16, 32, .. 8G CONSECUTIVE columns (mgpu_schedule) -- the order
+//     in which the leaves' sponges absorb them (hashing.rs:81-104) -- and device s owns `per` consecutive columns of each
+//     round; the first rounds are small so hashing starts after one column per device has been transformed and exchanged;
+//   * device g uploads and inverse-transforms its blocks, then PUSHES each block into every device's coefficient matrix
+//     with cudaMemcpyPeerAsync over NVLink on its own copy stream (the one real exchange of the path; no NCCL needed in
+//     one process);
+//   * device d owns coset blocks [d R/G, (d+1) R/G) = the contiguous leaf range [d N/G, (d+1) N/G): as soon as a round has
+//     landed (cross-device cudaStreamWaitEvent -- no host synchronisation anywhere in the flow) it low-degree-extends those
+//     columns into its leaf rows and advances its leaves' sponges while the next round is in flight;
+//   * digest layers up to the device's top layer, then the top-layer nodes (the cap entries whenever 2^cap_height >= G)
+//     are pushed to every device and the remaining layers, if any, are finished everywhere.
+// The host thread only enqueues; p2b_mgpu_synchronize() / the getters wait.
+#pragma once
+
+struct p2b_mgpu {
+  int n = 0;
+  std::vector<p2b_ctx*> ctx;
+  std::vector<cudaStream_t> xfer;                 // per device: the stream its peer pushes run on
+  std::vector<std::vector<cudaEvent_t>> ev_ifft;  // [device][round]
+  std::vector<std::vector<cudaEvent_t>> ev_push;  // [device][round]
+  std::vector<cudaEvent_t> ev_nodes, ev_t0, ev_t1, ev_done;
+  std::vector<u64*> cols;                         // per device: its column blocks [rounds * 8][n]
+  std::vector<u64> cols_elems;
+  std::vector<u64*> nodes_all;                    // per device: gathered top-layer nodes
+  std::vector<u64> nodes_elems;
+  bool peer_ok = true;
+};
+
+struct p2b_mgpu_batch {
+  p2b_mgpu* g = nullptr;
+  std::vector<p2b_batch*> shard;  // one per device, leaves [d N/G, (d+1) N/G)
+  p2b_batch_info info{};
+};
+
+// exchange rounds (mirrors sharded.exchange_schedule / local_layout in plonky2-gpu_b200/sharded.py)
+struct MgpuRound {
+  u64 col0, width, per, row0;  // columns [col0, col0 + width); device s owns [col0 + s*per, +per) clipped, at local rows [row0, row0 + per)
+};
+static std::vector<MgpuRound> mgpu_schedule(u64 P, int G, u64* rows_total) {
+  std::vector<MgpuRound> r;
+  u64 col0 = 0, w = 8, row0 = 0;
+  while (col0 < P) {
+    u64 width = std::min<u64>(w, P - col0), per = (width + G - 1) / G;
+    r.push_back(MgpuRound{col0, width, per, row0});
+    col0 += width;
+    row0 += per;
+    if (r.size() >= 2) w = std::min<u64>(2 * w, (u64)8 * G);
+  }
+  if (rows_total) *rows_total = row0;
+  return r;
+}
+
+static int mgpu_events(p2b_mgpu* g, int dev, size_t rounds) {
+  CUDA_TRY(cudaSetDevice(g->ctx[dev]->device));
+  while (g->ev_ifft[dev].size() < rounds) {
+    cudaEvent_t a, b;
+    CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    g->ev_ifft[dev].push_back(a);
+    g->ev_push[dev].push_back(b);
+  }
+  return P2B_OK;
+}
+
+extern "C" void p2b_mgpu_destroy(p2b_mgpu* g) {
+  if (!g) return;
+  for (int d = 0; d < g->n; d++) {
+    if (!g->ctx[d]) continue;
+    cudaSetDevice(g->ctx[d]->device);
+    if (g->xfer[d]) {
+      cudaStreamSynchronize(g->xfer[d]);
+      cudaStreamDestroy(g->xfer[d]);
+    }
+    cudaStreamSynchronize(g->ctx[d]->stream);
+    for (cudaEvent_t e : g->ev_ifft[d]) cudaEventDestroy(e);
+    for (cudaEvent_t e : g->ev_push[d]) cudaEventDestroy(e);
+    for (cudaEvent_t e : {g->ev_nodes[d], g->ev_t0[d], g->ev_t1[d], g->ev_done[d]})
+      if (e) cudaEventDestroy(e);
+    if (g->cols[d]) cudaFree(g->cols[d]);
+    if (g->nodes_all[d]) cudaFree(g->nodes_all[d]);
+    p2b_ctx_destroy(g->ctx[d]);
+  }
+  delete g;
+}
+
+extern "C" int p2b_mgpu_create(const int* devices, int n_dev, p2b_mgpu** out) {
+  if (!out) return fail(P2B_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  if (n_dev <= 0 || (n_dev & (n_dev - 1)) || n_dev > 64) return fail(P2B_ERR_INVALID, "device count %d must be a power of two in [1, 64]", n_dev);
+  p2b_mgpu* g = new (std::nothrow) p2b_mgpu();
+  if (!g) return fail(P2B_ERR_OOM, "host allocation failed");
+  g->n = n_dev;
+  g->ctx.assign(n_dev, nullptr);
+  g->xfer.assign(n_dev, nullptr);
+  g->ev_ifft.resize(n_dev);
+  g->ev_push.resize(n_dev);
+  g->ev_nodes.assign(n_dev, nullptr);
+  g->ev_t0.assign(n_dev, nullptr);
+  g->ev_t1.assign(n_dev, nullptr);
+  g->ev_done.assign(n_dev, nullptr);
+  g->cols.assign(n_dev, nullptr);
+  g->cols_elems.assign(n_dev, 0);
+  g->nodes_all.assign(n_dev, nullptr);
+  g->nodes_elems.assign(n_dev, 0);
+  auto body = [&]() -> int {
+    for (int d = 0; d < n_dev; d++) {
+      int dev = devices ? devices[d] : d;
+      for (int e = 0; e < d; e++)
+        if (g->ctx[e]->device == dev) return fail(P2B_ERR_INVALID, "device %d listed twice", dev);
+      P2B_TRY(p2b_ctx_create(dev, &g->ctx[d]));
+      CUDA_TRY(cudaStreamCreateWithFlags(&g->xfer[d], cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&g->ev_nodes[d], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&g->ev_done[d], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreate(&g->ev_t0[d]));
+      CUDA_TRY(cudaEventCreate(&g->ev_t1[d]));
+    }
+    // direct NVLink copies between every pair; the stream-ordered pools (batch arrays) must be mapped into the peers too
+    for (int a = 0; a < n_dev; a++) {
+      CUDA_TRY(cudaSetDevice(g->ctx[a]->device));
+      cudaMemPool_t pool;
+      CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, g->ctx[a]->device));
+      for (int b = 0; b < n_dev; b++) {
+        if (a == b) continue;
+        int can = 0;
+        CUDA_TRY(cudaDeviceCanAccessPeer(&can, g->ctx[a]->device, g->ctx[b]->device));
+        if (!can) {
+          g->peer_ok = false;  // copies still work (staged by the driver), only slower
+          continue;
+        }
+        cudaError_t e = cudaDeviceEnablePeerAccess(g->ctx[b]->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(P2B_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        cudaMemAccessDesc desc{};
+        desc.location.type = cudaMemLocationTypeDevice;
+        desc.location.id = g->ctx[b]->device;
+        desc.flags = cudaMemAccessFlagsProtReadWrite;
+        CUDA_TRY(cudaMemPoolSetAccess(pool, &desc, 1));
+      }
+    }
+    return P2B_OK;
+  };
+  int rc = body();
+  if (rc != P2B_OK) {
+    p2b_mgpu_destroy(g);
+    return rc;
+  }
+  *out = g;
+  return P2B_OK;
+}
+
+extern "C" int p2b_mgpu_device_count(const p2b_mgpu* g) { return g ? g->n : 0; }
+extern "C" p2b_ctx* p2b_mgpu_ctx(p2b_mgpu* g, int index) { return (g && index >= 0 && index < g->n) ? g->ctx[index] : nullptr; }
+extern "C" int p2b_mgpu_peer_access(const p2b_mgpu* g) { return g && g->peer_ok ? 1 : 0; }
+
+extern "C" int p2b_mgpu_synchronize(p2b_mgpu* g) {
+  if (!g) return fail(P2B_ERR_INVALID, "NULL argument");
+  for (int d = 0; d < g->n; d++) {
+    CUDA_TRY(cudaSetDevice(g->ctx[d]->device));
+    CUDA_TRY(cudaStreamSynchronize(g->xfer[d]));
+    P2B_TRY(p2b_ctx_synchronize(g->ctx[d]));
+  }
+  return P2B_OK;
+}
+
+// device-side stopwatch over all devices: start marks every main stream, stop returns the longest span in ms
+extern "C" int p2b_mgpu_timer_start(p2b_mgpu* g) {
+  if (!g) return fail(P2B_ERR_INVALID, "NULL argument");
+  for (int d = 0; d < g->n; d++) {
+    CUDA_TRY(cudaSetDevice(g->ctx[d]->device));
+    CUDA_TRY(cudaEventRecord(g->ev_t0[d], g->ctx[d]->stream));
+  }
+  return P2B_OK;
+}
+extern "C" int p2b_mgpu_timer_stop_ms(p2b_mgpu* g, float* ms_max) {
+  if (!g || !ms_max) return fail(P2B_ERR_INVALID, "NULL argument");
+  *ms_max = 0;
+  for (int d = 0; d < g->n; d++) {
+    CUDA_TRY(cudaSetDevice(g->ctx[d]->device));
+    CUDA_TRY(cudaEventRecord(g->ev_t1[d], g->ctx[d]->stream));
+  }
+  for (int d = 0; d < g->n; d++) {
+    CUDA_TRY(cudaSetDevice(g->ctx[d]->device));
+    CUDA_TRY(cudaEventSynchronize(g->ev_t1[d]));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, g->ev_t0[d], g->ev_t1[d]));
+    if (ms > *ms_max) *ms_max = ms;
+  }
+  return P2B_OK;
+}
+
+extern "C" void p2b_mgpu_batch_destroy(p2b_mgpu_batch* b) {
+  if (!b) return;
+  for (p2b_batch* s : b->shard)
+    if (s) {
+      cudaSetDevice(s->ctx->device);
+      batch_free(s);
+    }
+  delete b;
+}
+
+// where the caller's value columns live
+enum { P2B_MGPU_SRC_HOST = 0, P2B_MGPU_SRC_RESIDENT = 1 };
+
+// PolynomialBatch::from_values over all devices of `g` (fri/oracle.rs:709-731 / :279-545).
+//   src == HOST    : values = host [P][n] (pinned for overlap); uploaded block by block behind the transforms
+//   src == RESIDENT: the column blocks are already on their devices in the layout of p2b_mgpu_resident_cols()
+//                    (what a prover that generates its witness on the GPUs, or a benchmark with inputs in HBM, has)
+//   coeffs_host_out: NULL or host [P][n]; receives the coefficients (the reference keeps them host-side, oracle.rs:403-407)
+static int mgpu_commit(p2b_mgpu* g, int src, const u64* values, u32 k, u64 P, u32 rate_bits, u32 cap_height, u64* coeffs_host_out,
+                       p2b_mgpu_batch** out) {
+  if (!g || !out) return fail(P2B_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  const int G = g->n;
+  const u64 R = (u64)1 << rate_bits;
+  if ((u64)G > R) return fail(P2B_ERR_INVALID, "%d devices exceed the 2^rate_bits = %llu coset blocks", G, (unsigned long long)R);
+  if (P <= 4) return fail(P2B_ERR_UNSUPPORTED, "multi-device commit needs more than 4 polynomials (hash_or_noop copies shorter leaves)");
+  if (src == P2B_MGPU_SRC_HOST && !values) return fail(P2B_ERR_INVALID, "NULL values");
+  const u64 n = (u64)1 << k;
+  u64 rows_total = 0;
+  const std::vector<MgpuRound> sched = mgpu_schedule(P, G, &rows_total);
+  const u64 rounds = sched.size();
+  p2b_mgpu_batch* mb = new (std::nothrow) p2b_mgpu_batch();
+  if (!mb) return fail(P2B_ERR_OOM, "host allocation failed");
+  mb->g = g;
+  mb->shard.assign(G, nullptr);
+  auto body = [&]() -> int {
+    for (int d = 0; d < G; d++) {
+      p2b_ctx* c = g->ctx[d];
+      CUDA_TRY(cudaSetDevice(c->device));
+      P2B_TRY(mgpu_events(g, d, (size_t)rounds));
+      if (g->cols_elems[d] < rows_total * n) {
+        if (src == P2B_MGPU_SRC_RESIDENT) return fail(P2B_ERR_INVALID, "resident columns were not allocated for this shape (p2b_mgpu_resident_cols)");
+        if (g->cols[d]) {
+          CUDA_TRY(cudaDeviceSynchronize());
+          CUDA_TRY(cudaFree(g->cols[d]));
+          g->cols[d] = nullptr;
+        }
+        CUDA_TRY(cudaMalloc(&g->cols[d], rows_total * n * sizeof(u64)));
+        g->cols_elems[d] = rows_total * n;
+      }
+      P2B_TRY(ensure_scratch(c, (u64)G * 8 * n));
+      P2B_TRY(p2b_commit_blocks_begin(c, k, P, rate_bits, cap_height, (u64)d * (R / G), R / G, &mb->shard[d]));
+      // the peers push into this shard's coefficient matrix: its allocation must precede their copies
+      CUDA_TRY(cudaEventRecord(g->ev_done[d], c->stream));
+    }
+    for (int s = 0; s < G; s++)
+      for (int d = 0; d < G; d++) {
+        CUDA_TRY(cudaSetDevice(g->ctx[s]->device));
+        CUDA_TRY(cudaStreamWaitEvent(g->xfer[s], g->ev_done[d], 0));
+      }
+    auto slice = [&](const MgpuRound& r, int s, u64* c0, u64* nc) {
+      *c0 = std::min<u64>(r.col0 + (u64)s * r.per, r.col0 + r.width);
+      *nc = std::min<u64>(r.per, r.col0 + r.width - *c0);
+    };
+    auto absorb_round = [&](u64 j) -> int {
+      for (int d = 0; d < G; d++) {
+        p2b_ctx* c = g->ctx[d];
+        CUDA_TRY(cudaSetDevice(c->device));
+        for (int s = 0; s < G; s++) {
+          u64 c0, nc;
+          slice(sched[j], s, &c0, &nc);
+          if (nc) CUDA_TRY(cudaStreamWaitEvent(c->stream, g->ev_push[s][j], 0));
+        }
+        P2B_TRY(lde_and_absorb_group(mb->shard[d], sched[j].col0, sched[j].width, true));
+      }
+      return P2B_OK;
+    };
+    for (u64 j = 0; j < rounds; j++) {
+      for (int s = 0; s < G; s++) {
+        u64 c0, nc;
+        slice(sched[j], s, &c0, &nc);
+        if (!nc) continue;
+        p2b_ctx* c = g->ctx[s];
+        CUDA_TRY(cudaSetDevice(c->device));
+        u64* blk = g->cols[s] + sched[j].row0 * n;
+        if (src == P2B_MGPU_SRC_HOST) {
+          cudaEvent_t up = c->ev_copy[j % 14];
+          CUDA_TRY(cudaMemcpyAsync(blk, values + c0 * n, nc * n * sizeof(u64), cudaMemcpyHostToDevice, c->stream_h2d));
+          CUDA_TRY(cudaEventRecord(up, c->stream_h2d));
+          CUDA_TRY(cudaStreamWaitEvent(c->stream, up, 0));
+        }
+        P2B_TRY(run_ifft(c, blk, blk, c->scratch, k, nc));
+        CUDA_TRY(cudaEventRecord(g->ev_ifft[s][j], c->stream));
+        if (coeffs_host_out) {
+          CUDA_TRY(cudaStreamWaitEvent(c->stream_d2h, g->ev_ifft[s][j], 0));
+          CUDA_TRY(cudaMemcpyAsync(coeffs_host_out + c0 * n, blk, nc * n * sizeof(u64), cudaMemcpyDeviceToHost, c->stream_d2h));
+        }
+        CUDA_TRY(cudaStreamWaitEvent(g->xfer[s], g->ev_ifft[s][j], 0));
+        for (int dd = 0; dd < G; dd++) {
+          const int d = (s + dd) % G;  // stagger the destinations so the pushes of one round spread over the switch
+          CUDA_TRY(cudaMemcpyPeerAsync(mb->shard[d]->coeffs + c0 * n, g->ctx[d]->device, blk, c->device, nc * n * sizeof(u64), g->xfer[s]));
+        }
+        CUDA_TRY(cudaEventRecord(g->ev_push[s][j], g->xfer[s]));
+      }
+      if (j >= 1) P2B_TRY(absorb_round(j - 1));
+    }
+    P2B_TRY(absorb_round(rounds - 1));
+    // digest layers on every device, then the top-layer node exchange
+    u32 top = 0;
+    u64 count = 0;
+    for (int d = 0; d < G; d++) {
+      p2b_ctx* c = g->ctx[d];
+      CUDA_TRY(cudaSetDevice(c->device));
+      // lde_and_absorb_group hashed on stream2: join before the layers
+      CUDA_TRY(cudaEventRecord(c->ev_b, c->stream2));
+      CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_b, 0));
+      P2B_TRY(p2b_commit_blocks_finish(mb->shard[d]));
+      top = mb->shard[d]->top_layer;
+      count = mb->shard[d]->local_leaves >> top;
+    }
+    if (G > 1) {
+      for (int d = 0; d < G; d++) {
+        CUDA_TRY(cudaSetDevice(g->ctx[d]->device));
+        if (g->nodes_elems[d] < (u64)G * count * 4) {
+          if (g->nodes_all[d]) {
+            CUDA_TRY(cudaDeviceSynchronize());
+            CUDA_TRY(cudaFree(g->nodes_all[d]));
+          }
+          CUDA_TRY(cudaMalloc(&g->nodes_all[d], (u64)G * count * 4 * sizeof(u64)));
+          g->nodes_elems[d] = (u64)G * count * 4;
+        }
+      }
+      for (int s = 0; s < G; s++) {
+        p2b_ctx* c = g->ctx[s];
+        CUDA_TRY(cudaSetDevice(c->device));
+        u64* mine = g->nodes_all[s] + (u64)s * count * 4;
+        P2B_TRY(p2b_batch_export_nodes(mb->shard[s], top, (u64)s * count, count, mine));
+        CUDA_TRY(cudaEventRecord(g->ev_ifft[s][0], c->stream));
+        CUDA_TRY(cudaStreamWaitEvent(g->xfer[s], g->ev_ifft[s][0], 0));
+        for (int d = 0; d < G; d++)
+          if (d != s)
+            CUDA_TRY(cudaMemcpyPeerAsync(g->nodes_all[d] + (u64)s * count * 4, g->ctx[d]->device, mine, c->device, count * 4 * sizeof(u64), g->xfer[s]));
+        CUDA_TRY(cudaEventRecord(g->ev_nodes[s], g->xfer[s]));
+      }
+      for (int d = 0; d < G; d++) {
+        p2b_ctx* c = g->ctx[d];
+        CUDA_TRY(cudaSetDevice(c->device));
+        for (int s = 0; s < G; s++)
+          if (s != d) CUDA_TRY(cudaStreamWaitEvent(c->stream, g->ev_nodes[s], 0));
+        P2B_TRY(p2b_batch_import_nodes(mb->shard[d], top, 0, (u64)G * count, g->nodes_all[d]));
+        P2B_TRY(p2b_batch_finish_layers(mb->shard[d], top));
+      }
+    }
+    if (coeffs_host_out)
+      for (int d = 0; d < G; d++) {
+        CUDA_TRY(cudaSetDevice(g->ctx[d]->device));
+        CUDA_TRY(cudaEventRecord(g->ctx[d]->ev_a, g->ctx[d]->stream_d2h));
+        CUDA_TRY(cudaStreamWaitEvent(g->ctx[d]->stream, g->ctx[d]->ev_a, 0));
+      }
+    return P2B_OK;
+  };
+  int rc = body();
+  if (rc != P2B_OK) {
+    for (int d = 0; d < G; d++)
+      if (g->ctx[d]) {
+        cudaSetDevice(g->ctx[d]->device);
+        cudaDeviceSynchronize();
+      }
+    p2b_mgpu_batch_destroy(mb);
+    return rc;
+  }
+  mb->info = mb->shard[0]->info;
+  *out = mb;
+  return P2B_OK;
+}
+
+extern "C" int p2b_mgpu_commit_from_values(p2b_mgpu* g, const uint64_t* values_host, uint32_t degree_log, uint64_t num_polys,
+                                           uint32_t rate_bits, uint32_t cap_height, uint64_t* coeffs_host_out, p2b_mgpu_batch** out) {
+  return mgpu_commit(g, P2B_MGPU_SRC_HOST, values_host, degree_log, num_polys, rate_bits, cap_height, coeffs_host_out, out);
+}
+
+// Device-resident input: returns (allocating on first use) device `index`'s local buffer [rows_total][n] in the layout of
+// the exchange schedule: for round j (p2b_mgpu_round), rows [row0_j, row0_j + per_j) hold this device's columns
+// [col0_j + index * per_j, ...) of the value matrix (zero rows where the round is ragged).
+extern "C" int p2b_mgpu_resident_cols(p2b_mgpu* g, int index, uint32_t degree_log, uint64_t num_polys, uint64_t** d_cols_out,
+                                      uint64_t* rounds_out) {
+  if (!g || index < 0 || index >= g->n || !d_cols_out) return fail(P2B_ERR_INVALID, "bad argument");
+  const u64 n = (u64)1 << degree_log;
+  u64 rows_total = 0;
+  const u64 rounds = mgpu_schedule(num_polys, g->n, &rows_total).size();
+  CUDA_TRY(cudaSetDevice(g->ctx[index]->device));
+  if (g->cols_elems[index] < rows_total * n) {
+    if (g->cols[index]) {
+      CUDA_TRY(cudaDeviceSynchronize());
+      CUDA_TRY(cudaFree(g->cols[index]));
+      g->cols[index] = nullptr;
+    }
+    CUDA_TRY(cudaMalloc(&g->cols[index], rows_total * n * sizeof(u64)));
+    CUDA_TRY(cudaMemset(g->cols[index], 0, rows_total * n * sizeof(u64)));
+    g->cols_elems[index] = rows_total * n;
+  }
+  *d_cols_out = g->cols[index];
+  if (rounds_out) *rounds_out = rounds;
+  return P2B_OK;
+}
+// round j of the exchange schedule for (num_polys, this device count): columns [col0, col0 + width), `per` per device, at local
+// rows [row0, row0 + per); returns P2B_ERR_INVALID past the last round
+extern "C" int p2b_mgpu_round(const p2b_mgpu* g, uint64_t num_polys, uint64_t j, uint64_t* col0, uint64_t* width, uint64_t* per,
+                              uint64_t* row0) {
+  if (!g) return fail(P2B_ERR_INVALID, "NULL argument");
+  const std::vector<MgpuRound> sched = mgpu_schedule(num_polys, g->n, nullptr);
+  if (j >= sched.size()) return fail(P2B_ERR_INVALID, "round %llu past the %zu rounds of the schedule", (unsigned long long)j, sched.size());
+  if (col0) *col0 = sched[j].col0;
+  if (width) *width = sched[j].width;
+  if (per) *per = sched[j].per;
+  if (row0) *row0 = sched[j].row0;
+  return P2B_OK;
+}
+// NOTE: the transform is done in place -- the resident values are consumed (refill them before the next commit).
+extern "C" int p2b_mgpu_commit_resident(p2b_mgpu* g, uint32_t degree_log, uint64_t num_polys, uint32_t rate_bits, uint32_t cap_height,
+                                        uint64_t* coeffs_host_out, p2b_mgpu_batch** out) {
+  return mgpu_commit(g, P2B_MGPU_SRC_RESIDENT, nullptr, degree_log, num_polys, rate_bits, cap_height, coeffs_host_out, out);
+}
+
+extern "C" int p2b_mgpu_batch_get_info(const p2b_mgpu_batch* b, p2b_batch_info* out) {
+  if (!b || !out) return fail(P2B_ERR_INVALID, "NULL argument");
+  *out = b->info;
+  return P2B_OK;
+}
+extern "C" p2b_batch* p2b_mgpu_batch_shard(p2b_mgpu_batch* b, int index) {
+  return (b && index >= 0 && index < (int)b->shard.size()) ? b->shard[index] : nullptr;
+}
+// the full cap (identical on every device after the exchange); waits for the commit
+extern "C" int p2b_mgpu_batch_get_cap(const p2b_mgpu_batch* b, uint64_t* out) {
+  if (!b || !out) return fail(P2B_ERR_INVALID, "NULL argument");
+  P2B_TRY(p2b_mgpu_synchronize(b->g));
+  return p2b_batch_get_cap(b->shard[0], out);
+}
+// FRI query openings (fri/prover.rs:187-216): every index is served by the device that owns the leaf.
+extern "C" int p2b_mgpu_batch_open_rows(const p2b_mgpu_batch* b, const uint64_t* leaf_indices, uint64_t count, uint64_t* rows_out,
+                                        uint64_t* siblings_out) {
+  if (!b || !leaf_indices || !rows_out) return fail(P2B_ERR_INVALID, "NULL argument");
+  const u64 per = b->info.num_leaves / b->shard.size();
+  const u64 ll = b->info.leaf_len, layers = b->shard[0]->shape.sub_log;
+  P2B_TRY(p2b_mgpu_synchronize(b->g));
+  for (size_t d = 0; d < b->shard.size(); d++) {
+    std::vector<u64> idx;
+    std::vector<u64> slot;
+    for (u64 i = 0; i < count; i++) {
+      if (leaf_indices[i] >= b->info.num_leaves) return fail(P2B_ERR_INVALID, "leaf index %llu out of range", (unsigned long long)leaf_indices[i]);
+      if (leaf_indices[i] / per == d) {
+        idx.push_back(leaf_indices[i]);
+        slot.push_back(i);
+      }
+    }
+    if (idx.empty()) continue;
+    std::vector<u64> rows(idx.size() * ll), sibs(siblings_out ? idx.size() * layers * 4 : 0);
+    P2B_TRY(p2b_batch_open_rows(b->shard[d], idx.data(), idx.size(), rows.data(), siblings_out && layers ? sibs.data() : nullptr));
+    for (size_t t = 0; t < idx.size(); t++) {
+      memcpy(rows_out + slot[t] * ll, rows.data() + t * ll, ll * sizeof(u64));
+      if (siblings_out && layers) memcpy(siblings_out + slot[t] * layers * 4, sibs.data() + t * layers * 4, layers * 4 * sizeof(u64));
+    }
+  }
+  return P2B_OK;
+}
+// rows [first_leaf, first_leaf + count) of the LDE matrix, across shard boundaries
+extern "C" int p2b_mgpu_batch_get_leaves(const p2b_mgpu_batch* b, uint64_t first_leaf, uint64_t count, uint64_t* out) {
+  if (!b || !out) return fail(P2B_ERR_INVALID, "NULL argument");
+  if (first_leaf + count > b->info.num_leaves) return fail(P2B_ERR_INVALID, "leaf range out of bounds");
+  P2B_TRY(p2b_mgpu_synchronize(b->g));
+  const u64 per = b->info.num_leaves / b->shard.size();
+  u64 done = 0;
+  while (done < count) {
+    u64 leaf = first_leaf + done, d = leaf / per, take = std::min<u64>(count - done, (d + 1) * per - leaf);
+    P2B_TRY(p2b_batch_get_leaves(b->shard[d], leaf, take, out + done * b->info.leaf_len));
+    done += take;
+  }
+  return P2B_OK;
+}

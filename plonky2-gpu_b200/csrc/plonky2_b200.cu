@@ -1428,3 +1428,4 @@ extern "C" int p2b_partial_products_and_zs(p2b_ctx* c, const uint64_t* d_wires_v
 
 #include "fri_api.cuh"
 #include "compat.cuh"
+#include "mgpu.cuh"

@@ -100,50 +100,80 @@ def sharded_commit_from_values(engine, comm, values_shard, num_polys, n_log, rat
 SPONGE_RATE = 8
 
 
-def cyclic_column_blocks(num_polys, world, rank):
-    """Column blocks of SPONGE_RATE columns dealt round-robin: block q = columns [8q, 8q + 8) belongs to rank q % world and
-    is exchanged in round q // world, so that one all-gather round delivers 8 * world CONSECUTIVE columns -- the order in
-    which the leaves' sponges absorb them (hashing.rs:81-104).  Returns (rounds, [block index or None per round])."""
-    nblocks = -(-num_polys // SPONGE_RATE)
-    rounds = -(-nblocks // world)
-    mine = [j * world + rank if j * world + rank < nblocks else None for j in range(rounds)]
-    return rounds, mine
+def exchange_schedule(num_polys, world):
+    """Rounds of the pipelined exchange: [(col0, width, per_rank)].  Round j delivers the `width` CONSECUTIVE columns
+    [col0, col0 + width) -- the order in which the leaves' sponges absorb them (hashing.rs:81-104), so every width but the
+    last is a multiple of the sponge rate 8 -- of which rank r contributes [col0 + r * per_rank, col0 + (r + 1) * per_rank)
+    (clipped to the round).  Widths grow 8, 8, 16, 32, ... up to 8 * world: the first rounds are small so that hashing
+    starts after ONE column per rank has been uploaded, transformed, exchanged and extended (at 8 ranks the pipeline
+    prologue drops from 64 columns to 8), the later ones large so that launches and collectives stay few.
+    Mirrored in C++ by mgpu_schedule() (csrc/mgpu.cuh)."""
+    rounds, col0, w = [], 0, SPONGE_RATE
+    while col0 < num_polys:
+        width = min(w, num_polys - col0)
+        rounds.append((col0, width, -(-width // world)))
+        col0 += width
+        if len(rounds) >= 2:
+            w = min(2 * w, SPONGE_RATE * world)
+    return rounds
 
 
-def sharded_commit_from_values_pipelined(engine, comm, values_blocks, num_polys, n_log, rate_bits, cap_height,
+def local_layout(num_polys, world, rank):
+    """This rank's slice of every round: (rows_total, [(row0, c0, c1)] per round) -- its columns [c0, c1) of round j sit at
+    rows [row0, row0 + per_rank_j) of its local buffer [rows_total][n] (zero rows where the round is ragged)."""
+    row, out = 0, []
+    for col0, width, per in exchange_schedule(num_polys, world):
+        c0 = min(col0 + rank * per, col0 + width)
+        c1 = min(c0 + per, col0 + width)
+        out.append((row, c0, c1))
+        row += per
+    return row, out
+
+
+def pack_local(values, num_polys, world, rank):
+    """The rank's local buffer (numpy uint64 [rows_total][n]) from the full value matrix [P][n] (tests / examples)."""
+    rows, layout = local_layout(num_polys, world, rank)
+    buf = np.zeros((rows, values.shape[1]), dtype=np.uint64)
+    for row0, c0, c1 in layout:
+        buf[row0: row0 + (c1 - c0)] = values[c0:c1]
+    return buf
+
+
+def sharded_commit_from_values_pipelined(engine, comm, values_local, num_polys, n_log, rate_bits, cap_height,
                                          on_coeffs_ready=None, host_values=None):
     """Same result as sharded_commit_from_values with the exchange hidden behind the hashing.
-    values_blocks: this rank's column blocks, engine-native [rounds * 8][n]: rows [8j, 8j + 8) = block
-    cyclic_column_blocks(...)[1][j] (zero rows where the block is short or absent).  Steps: inverse NTT of the local
-    blocks; one asynchronous all-gather per round (NCCL runs them back to back on its own stream); as soon as round j has
-    landed its 8 * world consecutive coefficient columns are LDE'd into the leaf rows of this rank's coset blocks and
-    absorbed by the leaves' sponges (p2b_commit_blocks_absorb) while round j + 1 is still in flight; digest layers and
-    the top-layer node exchange as in the unpipelined flow."""
+    values_local: this rank's columns in the layout of local_layout() (engine-native [rows_total][n]).  Steps: inverse NTT
+    of the local columns; one asynchronous all-gather per round (NCCL runs them back to back on its own stream); as soon as
+    round j has landed its consecutive coefficient columns are LDE'd into the leaf rows of this rank's coset blocks and
+    absorbed by the leaves' sponges (p2b_commit_blocks_absorb) while round j + 1 is still in flight; digest layers and the
+    top-layer node exchange as in the unpipelined flow."""
     rank, world = comm.rank, comm.world
-    rounds, mine = cyclic_column_blocks(num_polys, world, rank)
+    sched = exchange_schedule(num_polys, world)
+    rows_total, layout = local_layout(num_polys, world, rank)
     b0, bcount = block_shard(rate_bits, world, rank)
     batch = engine.commit_begin(num_polys, n_log, rate_bits, cap_height, b0, bcount)
     pending = []
 
     def absorb(j):
-        cols = comm.wait(pending[j])                                    # [world * 8][n] = columns [8 world j, 8 world (j+1)) in order
-        col0 = j * world * SPONGE_RATE
-        engine.commit_absorb(batch, cols, col0, min(world * SPONGE_RATE, num_polys - col0))
+        cols = comm.wait(pending[j])                                    # [world * per_j][n]: the round's columns in order
+        col0, width, _ = sched[j]
+        engine.commit_absorb(batch, cols, col0, width)
 
-    # software pipeline over the rounds: (upload +) inverse NTT of block j -> its all-gather starts -> LDE + absorb of
-    # round j - 1 is enqueued, so the GPU hashes round j - 1 while round j is exchanged and block j + 1 is uploaded
+    # software pipeline over the rounds: (upload +) inverse NTT of this rank's slice of round j -> its all-gather starts ->
+    # LDE + absorb of round j - 1 is enqueued, so the GPU hashes round j - 1 while round j is exchanged and j + 1 uploads
     if host_values is None:
-        engine.ifft_columns(values_blocks, rounds * SPONGE_RATE, n_log)  # device-resident input: all local blocks at once (zero rows stay zero)
-    for j in range(rounds):
-        blk = values_blocks[j * SPONGE_RATE:(j + 1) * SPONGE_RATE]
+        engine.ifft_columns(values_local, rows_total, n_log)            # device-resident input: all local rows at once (zero rows stay zero)
+    for j, (row0, c0, c1) in enumerate(layout):
+        per = sched[j][2]
+        blk = values_local[row0:row0 + per]
         if host_values is not None:
-            engine.ifft_columns_from_host(host_values[j * SPONGE_RATE:(j + 1) * SPONGE_RATE], blk, SPONGE_RATE, n_log, groups=1)
+            engine.ifft_columns_from_host(host_values[row0:row0 + per], blk, per, n_log, groups=1)
         pending.append(comm.all_gather_async(blk))
         if j >= 1:
             absorb(j - 1)
     if on_coeffs_ready is not None:
-        on_coeffs_ready(values_blocks)
-    absorb(rounds - 1)
+        on_coeffs_ready(values_local)
+    absorb(len(sched) - 1)
     batch = engine.commit_finish(batch)
     top = local_top_layer(n_log, rate_bits, cap_height, world)
     count = ((1 << (n_log + rate_bits)) // world) >> top
@@ -175,33 +205,56 @@ def sharded_open_rows(engine, comm, batch, indices, n_log, rate_bits, cap_height
 # GPU engine / torch.distributed communicator
 # ---------------------------------------------------------------------------------------------------------------
 class GpuEngine:
-    """The C ABI (libplonky2_b200.so) on torch CUDA tensors (torch is plumbing: device memory + NCCL)."""
+    """The C ABI (libplonky2_b200.so) on torch CUDA tensors (torch is plumbing: device memory + NCCL).
+
+    No host synchronisation between the phases: work is handed between torch's current stream (where NCCL collectives are
+    ordered) and the library's stream with CUDA events in both directions (`_sync_in` / `_sync_out`); tensors the library
+    reads asynchronously are kept referenced until `synchronize()`.  The caller waits once, at the end of a commit
+    (`engine.synchronize()`), or implicitly through a getter that copies to the host."""
 
     def __init__(self, ctx):
         import torch
         from . import lib, _check, PolynomialBatch
         self.torch, self.lib, self._check, self._PB, self.ctx = torch, lib(), _check, PolynomialBatch, ctx
+        self.lib.p2b_ctx_stream.restype = C.c_void_p
+        self._lib_stream = torch.cuda.ExternalStream(self.lib.p2b_ctx_stream(ctx.handle))
+        self._copy_stream = torch.cuda.Stream()
+        self._keep = []
 
-    def _sync_in(self):
-        self.torch.cuda.current_stream().synchronize()  # torch-side producers done before the library's stream reads
+    def synchronize(self):
+        """Wait for everything enqueued so far and release the tensors the library was still reading."""
+        self.ctx.synchronize()
+        self.torch.cuda.current_stream().synchronize()
+        self._copy_stream.synchronize()
+        self._keep = []
+
+    def _sync_in(self, *tensors):
+        """torch-side producers (NCCL, copies) -> the library's stream: a device-side wait, the host does not block."""
+        ev = self.torch.cuda.Event()
+        ev.record(self.torch.cuda.current_stream())
+        self._lib_stream.wait_event(ev)
+        self._keep.extend(tensors)
+
+    def _sync_out(self):
+        """the library's results -> torch's current stream (the next collective is ordered behind them)."""
+        ev = self.torch.cuda.Event()
+        ev.record(self._lib_stream)
+        self.torch.cuda.current_stream().wait_event(ev)
 
     def ifft_columns(self, t, ncols, n_log):
         if ncols == 0:
             return
-        self._sync_in()
+        self._sync_in(t)
         self._check(self.lib.p2b_ifft_batch(self.ctx.handle, t.data_ptr(), t.data_ptr(), n_log, ncols))
-        self.ctx.synchronize()
+        self._sync_out()
 
     def ifft_columns_from_host(self, host_t, t, ncols, n_log, groups=8):
         """H2D on a copy stream in column groups; the library's stream waits for each group's event and transforms it."""
         if ncols == 0:
             return
         torch = self.torch
-        if not hasattr(self, "_copy_stream"):
-            self._copy_stream = torch.cuda.Stream()
-            self.lib.p2b_ctx_stream.restype = C.c_void_p
-            self._lib_stream = torch.cuda.ExternalStream(self.lib.p2b_ctx_stream(self.ctx.handle))
-        self._sync_in()
+        self._sync_in(t)
+        self._copy_stream.wait_stream(torch.cuda.current_stream())
         for g in range(groups):
             a, b = ncols * g // groups, ncols * (g + 1) // groups
             if a == b:
@@ -212,10 +265,10 @@ class GpuEngine:
                 ev.record(self._copy_stream)
             self._lib_stream.wait_event(ev)
             self._check(self.lib.p2b_ifft_batch(self.ctx.handle, t[a:b].data_ptr(), t[a:b].data_ptr(), n_log, b - a))
-        self.ctx.synchronize()
+        self._sync_out()
 
     def commit_blocks(self, coeffs, num_polys, n_log, rate_bits, cap_height, b0, bcount):
-        self._sync_in()
+        self._sync_in(coeffs)
         h = C.c_void_p()
         self._check(self.lib.p2b_commit_blocks(self.ctx.handle, coeffs.data_ptr(), n_log, num_polys, rate_bits, cap_height,
                                                None, b0, bcount, C.byref(h)))
@@ -224,34 +277,30 @@ class GpuEngine:
     def commit_begin(self, num_polys, n_log, rate_bits, cap_height, b0, bcount):
         h = C.c_void_p()
         self._check(self.lib.p2b_commit_blocks_begin(self.ctx.handle, n_log, num_polys, rate_bits, cap_height, b0, bcount, C.byref(h)))
-        self._keep = []
         return h
 
     def commit_absorb(self, h, cols, col0, ncols):
-        self._sync_in()          # the all-gather that produced `cols` has completed (host wait; the previous group's kernels keep running)
-        self._keep.append(cols)  # the library reads `cols` asynchronously on its stream
+        self._sync_in(cols)      # ordered behind the all-gather that produced `cols`; the previous group's kernels keep running
         self._check(self.lib.p2b_commit_blocks_absorb(h, cols.data_ptr(), col0, ncols))
 
     def commit_finish(self, h):
         self._check(self.lib.p2b_commit_blocks_finish(h))
-        b = self._PB(self.ctx, h.value)
-        self.ctx.synchronize()
-        self._keep = []
-        return b
+        return self._PB(self.ctx, h.value)
 
     def export_nodes(self, batch, layer, first, count):
         out = self.torch.empty((count, 4), dtype=self.torch.int64, device="cuda")
+        self._sync_in(out)
         self._check(self.lib.p2b_batch_export_nodes(batch.handle, layer, first, count, out.data_ptr()))
-        self.ctx.synchronize()
+        self._sync_out()
         return out
 
     def import_nodes(self, batch, layer, first, count, t):
-        self._sync_in()
+        self._sync_in(t)
         self._check(self.lib.p2b_batch_import_nodes(batch.handle, layer, first, count, t.data_ptr()))
 
     def finish_layers(self, batch, from_layer):
         self._check(self.lib.p2b_batch_finish_layers(batch.handle, from_layer))
-        self.ctx.synchronize()
+        self._sync_out()
 
     def cap(self, batch):
         return batch.cap()

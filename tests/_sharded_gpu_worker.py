@@ -46,14 +46,9 @@ def main():
         qrows, qsibs = sharded.sharded_open_rows(engine, comm, b, qidx, n_log, rate_bits, cap_height, P)
         for x, r, sb in zip(qidx, qrows, qsibs):
             good = good and np.array_equal(r, ref.leaves[x]) and np.array_equal(sb, oracle.merkle_prove(ref.digests, N, cap_height, x))
-        # pipelined variant: cyclic 8-column blocks, exchange overlapped with LDE + progressive leaf hashing
+        # pipelined variant: growing exchange rounds, exchange overlapped with LDE + progressive leaf hashing
         if P > 4:
-            rounds, mine = sharded.cyclic_column_blocks(P, world, rank)
-            blocks = np.zeros((rounds * 8, 1 << n_log), dtype=np.uint64)
-            for j, qb in enumerate(mine):
-                if qb is not None:
-                    cols = values[8 * qb: min(8 * qb + 8, P)]
-                    blocks[8 * j: 8 * j + cols.shape[0]] = cols
+            blocks = sharded.pack_local(values, P, world, rank)
             tb = torch.from_numpy(blocks.view(np.int64)).cuda()
             pb = sharded.sharded_commit_from_values_pipelined(engine, comm, tb, P, n_log, rate_bits, cap_height)
             good = good and np.array_equal(pb.cap(), ref.cap) and np.array_equal(pb.polynomials(), ref.coeffs)

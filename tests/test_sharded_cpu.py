@@ -141,14 +141,23 @@ class OracleEngine:
         return t.numpy().view(np.uint64)
 
 
-def test_cyclic_column_blocks():
-    # 135 columns = 17 blocks of 8 on 8 ranks: 3 rounds, rank 0 holds blocks 0, 8, 16, rank 1 blocks 1, 9 and nothing in round 2
-    assert sharded.cyclic_column_blocks(135, 8, 0) == (3, [0, 8, 16])
-    assert sharded.cyclic_column_blocks(135, 8, 1) == (3, [1, 9, None])
-    assert sharded.cyclic_column_blocks(135, 2, 1) == (9, [1, 3, 5, 7, 9, 11, 13, 15, None])
-    assert sharded.cyclic_column_blocks(5, 4, 0) == (1, [0])
-    seen = sorted(q for r in range(4) for q in sharded.cyclic_column_blocks(135, 4, r)[1] if q is not None)
-    assert seen == list(range(17))
+def test_exchange_schedule():
+    # 135 columns on 8 ranks: rounds of 8, 8, 16, 32, 64, 7 columns; rank r contributes `per` consecutive columns of each
+    assert sharded.exchange_schedule(135, 8) == [(0, 8, 1), (8, 8, 1), (16, 16, 2), (32, 32, 4), (64, 64, 8), (128, 7, 1)]
+    assert sharded.exchange_schedule(135, 2)[:4] == [(0, 8, 4), (8, 8, 4), (16, 16, 8), (32, 16, 8)]
+    assert sharded.exchange_schedule(5, 4) == [(0, 5, 2)]
+    for P, world in [(135, 8), (135, 4), (135, 2), (234, 8), (400, 8), (9, 2), (5, 4), (16, 8)]:
+        sched = sharded.exchange_schedule(P, world)
+        assert [r[0] for r in sched] == [sum(x[1] for x in sched[:j]) for j in range(len(sched))] and sum(r[1] for r in sched) == P
+        assert all(w % 8 == 0 for _, w, _ in sched[:-1])                      # sponge-rate aligned except the last round
+        covered = []
+        for j, (col0, width, per) in enumerate(sched):
+            for r in range(world):
+                rows, layout = sharded.local_layout(P, world, r)
+                row0, c0, c1 = layout[j]
+                assert c1 - c0 <= per and row0 == sum(x[2] for x in sched[:j])
+                covered += list(range(c0, c1))
+        assert covered == list(range(P))                                      # rank-major order inside a round == column order
 
 
 def _free_port():
@@ -184,13 +193,8 @@ def _worker(rank, world, port, n_log, P, rate_bits, cap_height, q):
         for x, r, sb in zip(idx, rows, sibs):
             ok = ok and np.array_equal(r, ref.leaves[x]) and oracle.merkle_verify(r, x, ref.cap, sb)
             ok = ok and np.array_equal(sb, oracle.merkle_prove(ref.digests, N, cap_height, x))
-        # pipelined variant (cyclic 8-column blocks, one all-gather round per group): same cap, coefficients, leaves
-        rounds, mine = sharded.cyclic_column_blocks(P, world, rank)
-        blocks = np.zeros((rounds * 8, 1 << n_log), dtype=np.uint64)
-        for j, qb in enumerate(mine):
-            if qb is not None:
-                cols = values[8 * qb: min(8 * qb + 8, P)]
-                blocks[8 * j: 8 * j + cols.shape[0]] = cols
+        # pipelined variant (growing exchange rounds, one all-gather per round): same cap, coefficients, leaves
+        blocks = sharded.pack_local(values, P, world, rank)
         if P > 4:
             pb = sharded.sharded_commit_from_values_pipelined(OracleEngine(), comm, torch.from_numpy(blocks.view(np.int64)), P, n_log,
                                                               rate_bits, cap_height)
