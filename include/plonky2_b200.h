@@ -57,6 +57,13 @@ const char* p2b_version(void);
  * (plonky2/src/fri/oracle.rs:75-109: streams + root tables + shift powers + one big cache buffer).
  * ------------------------------------------------------------------------------------------------- */
 int p2b_ctx_create(int device /* -1 = current */, p2b_ctx** out);
+/* Stage tracing after the reference's TimingTree (plonky2/src/util/timing.rs:8-192): every stage the library enqueues carries
+ * the name of the reference's `timed!` scope ("IFFT", "FFT + blinding", "build Merkle tree: ...", fri/oracle.rs:717-966;
+ * "compute quotient polys", "compute partial products", "construct the opening set", "compute opening proofs",
+ * plonk/prover.rs:112-236) as an NVTX range (visible to nsys / ncu) and, once enabled here, as a CUDA-event pair.
+ * p2b_ctx_trace_report synchronises and writes "name\tcalls\ttotal_ms\n" per stage, then clears the record. */
+int p2b_ctx_trace(p2b_ctx* ctx, int enable);
+int p2b_ctx_trace_report(p2b_ctx* ctx, char* buf, uint64_t buf_len);
 void p2b_ctx_destroy(p2b_ctx* ctx);
 /* The CUDA stream (cudaStream_t) the context launches on; callers may enqueue their own copies on it. */
 void* p2b_ctx_stream(p2b_ctx* ctx);

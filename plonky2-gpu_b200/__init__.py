@@ -144,6 +144,8 @@ def lib():
         "p2b_ctx_synchronize": (i, [vp]),
         "p2b_ctx_launch_count": (u64, [vp]),
         "p2b_ctx_time_leaf_hash": (i, [vp, i]),
+        "p2b_ctx_trace": (i, [vp, i]),
+        "p2b_ctx_trace_report": (i, [vp, C.c_char_p, u64]),
         "p2b_ctx_debug_force_exact_redo": (i, [vp, i]),
         "p2b_ctx_leaf_hash_time": (i, [vp, C.POINTER(C.c_double), C.POINTER(u64)]),
         "p2b_commit_from_values": (i, [vp, vp, i, u32, u64, u32, u32, vp, i, C.POINTER(vp)]),
@@ -322,6 +324,20 @@ class Context:
 
     def debug_force_exact_redo(self, enable=True):
         _check(lib().p2b_ctx_debug_force_exact_redo(self.handle, 1 if enable else 0))
+
+    def trace(self, enable=True):
+        """Per-stage device timing under the reference's TimingTree scope names (util/timing.rs:8-192)."""
+        _check(lib().p2b_ctx_trace(self.handle, 1 if enable else 0))
+
+    def trace_report(self):
+        """[(stage name, calls, total ms)] since tracing was enabled / last reported."""
+        buf = C.create_string_buffer(1 << 16)
+        _check(lib().p2b_ctx_trace_report(self.handle, buf, len(buf)))
+        out = []
+        for line in buf.value.decode().splitlines():
+            name, calls, ms = line.split("\t")
+            out.append((name, int(calls), float(ms)))
+        return out
 
     def time_leaf_hash(self, enable=True):
         _check(lib().p2b_ctx_time_leaf_hash(self.handle, 1 if enable else 0))

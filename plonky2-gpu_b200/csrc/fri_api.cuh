@@ -67,6 +67,7 @@ static int fri_challenger_step(p2b_ctx* c, fri::Challenger* d_ch, const u64* obs
 extern "C" int p2b_eval_openings(p2b_ctx* c, const p2b_batch* b, const uint64_t point[2], uint64_t* out) {
   if (!c || !b || !point || !out) return fail(P2B_ERR_INVALID, "NULL argument");
   if (!b->coeffs) return fail(P2B_ERR_INVALID, "batch holds no coefficients");
+  Stage stage(c, c->stream, "construct the opening set");   // plonk/prover.rs:208-222
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
   const u64 n = (u64)1 << b->info.degree_log, P = b->info.num_polys;
@@ -99,6 +100,7 @@ extern "C" int p2b_fri_prove_openings(p2b_ctx* c, const p2b_batch* const* oracle
   if (!c || !oracles || !batches || !challenger || !params || !out) return fail(P2B_ERR_INVALID, "NULL argument");
   *out = nullptr;
   if (num_oracles == 0 || num_batches == 0) return fail(P2B_ERR_INVALID, "no oracles / no opening batches");
+  Stage stage(c, c->stream, "compute opening proofs");   // plonk/prover.rs:224-236
   if (challenger->input_len >= 8 || challenger->output_len > 8) return fail(P2B_ERR_INVALID, "challenger buffers out of range");
   if (params->num_reductions && !params->reduction_arity_bits) return fail(P2B_ERR_INVALID, "NULL reduction_arity_bits");
   const u32 k = params->degree_bits, rate_bits = params->rate_bits, cap_height = params->cap_height;

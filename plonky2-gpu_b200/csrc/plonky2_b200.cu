@@ -15,6 +15,7 @@
 //   cap     [2^c][4]
 // plus a context-owned scratch [P][n] that holds one coset block between its NTT passes.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX3: ranges cost nothing unless a profiler injects its library
 
 #include <cstdarg>
 #include <cstdio>
@@ -119,6 +120,36 @@ struct p2b_ctx {
   size_t hash_events_used = 0;
   int sm_count = 148;
   size_t smem_optin = 0;
+  // stage tracing (p2b_ctx_trace): the reference's TimingTree scopes (plonky2/src/util/timing.rs:8-192; "IFFT",
+  // "FFT + blinding", "build Merkle tree" at fri/oracle.rs:717-966, ...) as CUDA-event pairs on the launching stream
+  bool trace = false;
+  struct TraceSpan { const char* name; cudaEvent_t a, b; };
+  std::vector<TraceSpan> spans;
+  size_t spans_used = 0;
+};
+
+// RAII stage marker: an NVTX range around the host-side enqueue (shows up in nsys / ncu timelines) and, when tracing is
+// enabled on the context, an event pair on `st` whose elapsed time p2b_ctx_trace_report() sums per stage name.
+struct Stage {
+  p2b_ctx* c;
+  cudaStream_t st;
+  p2b_ctx::TraceSpan* span = nullptr;
+  Stage(p2b_ctx* c_, cudaStream_t st_, const char* name) : c(c_), st(st_) {
+    nvtxRangePushA(name);
+    if (!c->trace) return;
+    if (c->spans_used == c->spans.size()) {
+      p2b_ctx::TraceSpan sp{name, nullptr, nullptr};
+      if (cudaEventCreate(&sp.a) != cudaSuccess || cudaEventCreate(&sp.b) != cudaSuccess) return;
+      c->spans.push_back(sp);
+    }
+    span = &c->spans[c->spans_used++];
+    span->name = name;
+    cudaEventRecord(span->a, st);
+  }
+  ~Stage() {
+    if (span) cudaEventRecord(span->b, st);
+    nvtxRangePop();
+  }
 };
 
 static int ensure_scratch(p2b_ctx* c, u64 elems) {
@@ -241,6 +272,10 @@ extern "C" void p2b_ctx_destroy(p2b_ctx* c) {
   }
   for (cudaEvent_t e : c->ev_copy)
     if (e) cudaEventDestroy(e);
+  for (auto& sp : c->spans) {
+    cudaEventDestroy(sp.a);
+    cudaEventDestroy(sp.b);
+  }
   if (c->stream_h2d) cudaStreamDestroy(c->stream_h2d);
   if (c->stream_d2h) cudaStreamDestroy(c->stream_d2h);
   if (c->owns_streams) {
@@ -260,6 +295,48 @@ extern "C" int p2b_ctx_synchronize(p2b_ctx* c) {
   return P2B_OK;
 }
 extern "C" uint64_t p2b_ctx_launch_count(const p2b_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int p2b_ctx_trace(p2b_ctx* c, int enable) {
+  if (!c) return fail(P2B_ERR_INVALID, "NULL context");
+  c->trace = enable != 0;
+  c->spans_used = 0;
+  return P2B_OK;
+}
+// Synchronises the context and writes one line per stage, "name<TAB>calls<TAB>total ms", in first-seen order.  Stages on
+// different streams overlap (leaf hashing runs beside the next block's NTT), so the totals can exceed the wall time.
+extern "C" int p2b_ctx_trace_report(p2b_ctx* c, char* buf, uint64_t buf_len) {
+  if (!c || !buf || buf_len == 0) return fail(P2B_ERR_INVALID, "NULL argument");
+  P2B_TRY(p2b_ctx_synchronize(c));
+  std::vector<const char*> names;
+  std::vector<double> ms_sum;
+  std::vector<u64> calls;
+  for (size_t i = 0; i < c->spans_used; i++) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->spans[i].a, c->spans[i].b) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    size_t k = 0;
+    while (k < names.size() && strcmp(names[k], c->spans[i].name)) k++;
+    if (k == names.size()) {
+      names.push_back(c->spans[i].name);
+      ms_sum.push_back(0);
+      calls.push_back(0);
+    }
+    ms_sum[k] += ms;
+    calls[k]++;
+  }
+  std::string out;
+  char line[256];
+  for (size_t k = 0; k < names.size(); k++) {
+    snprintf(line, sizeof(line), "%s\t%llu\t%.4f\n", names[k], (unsigned long long)calls[k], ms_sum[k]);
+    out += line;
+  }
+  if (out.size() + 1 > buf_len) return fail(P2B_ERR_INVALID, "trace report needs %zu bytes", out.size() + 1);
+  memcpy(buf, out.c_str(), out.size() + 1);
+  c->spans_used = 0;
+  return P2B_OK;
+}
 extern "C" int p2b_ctx_debug_force_exact_redo(p2b_ctx* c, int enable) {
   if (!c) return fail(P2B_ERR_INVALID, "ctx is NULL");
   c->debug_force_redo = enable != 0;
@@ -355,6 +432,7 @@ static int launch_strided(p2b_ctx* c, cudaStream_t st, const ntt::PassArgs& a, c
 // ======================================================================================================
 static int run_ifft(p2b_ctx* c, const u64* src, u64* dst, u64* tmp, u32 k, u64 P) {
   if (P == 0) return P2B_OK;
+  Stage stage(c, c->stream, "IFFT");   // fri/oracle.rs:717-721
   P2B_TRY(ensure_twiddles(c, k > 0 ? k - 1 : 0));
   Plan pl = make_plan(k);
   const u64 n = (u64)1 << k;
@@ -409,6 +487,7 @@ static ntt::LevelScale lde_scale(u32 k, u64 shift = hostf::COSET_SHIFT) {
 // One coset block b of the LDE: coeffs [P][n] -> rows [b*n, (b+1)*n) of leaves (row-major).
 static int run_lde_block(p2b_ctx* c, cudaStream_t st, const u64* coeffs, u64 coeffs_cs, u64* tmp, u32 k, u64 P,
                          u64 b, const ntt::LevelScale& sc, u64* leaves, u64 row_stride, u64 col0, u64 row0) {
+  Stage stage(c, st, "FFT + blinding");   // fri/oracle.rs:927-931 (LDE of one coset block, written as leaf rows)
   Plan pl = make_plan(k);
   const u64 n = (u64)1 << k;
   ntt::PassArgs a{};
@@ -453,6 +532,7 @@ static int launch_hash_leaves(p2b_ctx* c, cudaStream_t st, const u64* leaves, u6
                               u32 leaf_len, u64 first_leaf, u64 count, const merkle::TreeShape& shape, u64* digests,
                               u64* cap) {
   if (count == 0) return P2B_OK;
+  Stage stage(c, st, "build Merkle tree: leaf hashes");   // fri/oracle.rs:962-966, merkle_tree.rs:210-244
   unsigned blocks = (unsigned)((count + P2B_HASH_BLOCK - 1) / P2B_HASH_BLOCK);
   // `leaves` points at the first leaf of this launch; first_leaf is its global index in the tree
   std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
@@ -477,6 +557,7 @@ static int launch_hash_leaves(p2b_ctx* c, cudaStream_t st, const u64* leaves, u6
 // `from_layer`.  Returns the last layer computed (== shape.sub_log when the range reaches the cap).
 static int launch_layers(p2b_ctx* c, cudaStream_t st, const merkle::TreeShape& shape, u64* digests, u64* cap,
                          u64 leaf0, u64 leaf1, u32 from_layer, u32* top_layer) {
+  Stage stage(c, st, "build Merkle tree: digest layers");
   u32 l = from_layer;
   while (l < shape.sub_log) {
     u64 span = (u64)1 << (l + 1);
@@ -819,6 +900,7 @@ static int lde_and_absorb_group(p2b_batch* b, u64 col0, u64 ncols, bool hash_on_
     hs = c->stream2;
   }
   const u64 count = b->local_leaves;
+  Stage stage(c, hs, "build Merkle tree: leaf hashes");
   unsigned blocks = (unsigned)((count + P2B_HASH_BLOCK - 1) / P2B_HASH_BLOCK);
   std::pair<cudaEvent_t, cudaEvent_t>* ev = nullptr;
   if (c->time_hash) {
@@ -1209,6 +1291,7 @@ static int quotient_impl(p2b_ctx* c, const p2b_circuit* circ, const u64* d_wires
                          u64 zs_stride, const u64* d_cs, u64 cs_stride, const u64* pih, const u64* betas, const u64* gammas,
                          const u64* alphas, u64* d_values_out, u64* d_coeffs_out, u64* d_rows_out) {
   if (!c || !circ || !d_wires || !d_zs_pp || !d_cs || !pih || !betas || !gammas || !alphas) return fail(P2B_ERR_INVALID, "NULL argument");
+  Stage stage(c, c->stream, "compute quotient polys");   // plonk/prover.rs:187-196
   if (!circ->gates && circ->num_gates) return fail(P2B_ERR_INVALID, "NULL gate list");
   if (!circ->k_is && circ->num_routed_wires) return fail(P2B_ERR_INVALID, "NULL k_is");
   const u32 nc = circ->num_challenges, qdf = circ->quotient_degree_factor;
@@ -1384,6 +1467,7 @@ extern "C" int p2b_partial_products_and_zs(p2b_ctx* c, const uint64_t* d_wires_v
                                            uint32_t num_challenges, const uint64_t* k_is, const uint64_t* betas,
                                            const uint64_t* gammas, uint64_t* d_out) {
   if (!c || !d_wires_values || !d_sigma_values || !k_is || !betas || !gammas || !d_out) return fail(P2B_ERR_INVALID, "NULL argument");
+  Stage stage(c, c->stream, "compute partial products");   // plonk/prover.rs:112-117
   if (degree_bits > 32) return fail(P2B_ERR_INVALID, "degree_bits exceeds the field's two-adicity 32");
   if (num_challenges == 0 || num_challenges > (u32)perm::MAX_CH) return fail(P2B_ERR_INVALID, "num_challenges must be in [1, %d]", perm::MAX_CH);
   if (quotient_degree_factor < 2) return fail(P2B_ERR_INVALID, "quotient_degree_factor must be at least 2");

@@ -101,3 +101,17 @@ def test_legacy_symbols_from_two_host_threads(ctx):
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert errs == [None, None]
+
+
+def test_stage_trace_names_follow_the_reference_timing_tree(ctx):
+    """p2b_ctx_trace: stages carry the reference's `timed!` scope names (fri/oracle.rs:717-966)."""
+    rng = np.random.default_rng(2)
+    values = rng.integers(0, P_, size=(20, 1 << 10), dtype=np.uint64)
+    ctx.trace(True)
+    b = p2b.PolynomialBatch.from_values(ctx, values, 3, 4)
+    rep = dict((name, (calls, ms)) for name, calls, ms in ctx.trace_report())
+    ctx.trace(False)
+    b.close()
+    for name in ("IFFT", "FFT + blinding", "build Merkle tree: leaf hashes", "build Merkle tree: digest layers"):
+        assert name in rep and rep[name][0] >= 1 and rep[name][1] > 0.0
+    assert rep["FFT + blinding"][0] % 8 == 0        # one LDE per coset block (and per column group of the pipelined upload)
