@@ -56,6 +56,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="commit", choices=["commit", "prove-ecc", "prove-recursion"],
+                    help="commit = the headline (BASELINE.json configs[1], or configs[4] sizes with --n-log/--polys); prove-* = the "
+                         "prove() data path on the configs[3] / configs[2] shapes (single GPU)")
     ap.add_argument("--n-log", type=int, default=20, help="log2 rows (development override; the judged run uses 20)")
     ap.add_argument("--polys", type=int, default=135)
     ap.add_argument("--cpu-sample-log", type=int, default=0,
@@ -523,6 +526,66 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_prove(args):
+    """--workload prove-ecc / prove-recursion: BASELINE.json's "e2e prove s" on the config 4 / config 3 shapes -- every stage of
+    prove() between the witness and the proof's field elements, on the device (plonky2-gpu_b200/pipeline.py).  One JSON line."""
+    import torch
+    import plonky2_gpu_b200 as p2b
+    from plonky2_gpu_b200.pipeline import ProvePipeline, STAGES
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    kind = "ecc" if args.workload == "prove-ecc" else "recursion"
+    n_log = args.n_log if any(a.startswith("--n-log") for a in sys.argv) else (17 if kind == "ecc" else 16)
+    p2b.build()
+    ctx = p2b.Context(0)
+    # parity preflight on a 2^8-row instance of the same gate set: quotient values at sampled points == CPU oracle
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from tests.test_gpu_configs import _oracle_circuit
+    from oracle import quotient as Q
+    import oracle
+    small = ProvePipeline(ctx, kind, 8)
+    _, keep = small.prove(keep=True)
+    circ = _oracle_circuit(small)
+    pts = [0, 1, 77, small.size - 1]
+    need = sorted(set(r for i in pts for r in Q.quotient_point_rows(circ, i)))
+    rows = {name: dict(zip(need, b.open_rows(need, with_proofs=False)[0])) for name, b in (("w", keep["b_w"]), ("z", keep["b_z"]), ("cs", small.b_cs))}
+    want = Q.compute_quotient_values(circ, rows["w"], rows["z"], rows["cs"], small.pih, small.betas, small.gammas, small.alphas, points=pts)
+    qv = keep["quotient_values"].to_host(small.nc * small.size).reshape(small.nc, small.size)
+    if any(int(qv[c][i]) != wv[c] for i, wv in zip(pts, want) for c in range(small.nc)):
+        raise SystemExit("bench.py: parity preflight failed (quotient values differ from the CPU oracle)")
+    keep["proof"].close()
+    for k in ("b_w", "b_z", "b_q"):
+        keep[k].close()
+    small.close()
+    pipe = ProvePipeline(ctx, kind, n_log)
+    for _ in range(max(args.warmup, 3)):
+        pipe.prove()
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.3)
+    times, walls = {}, []
+    launches0 = ctx.launch_count
+    for _ in range(args.steps):
+        walls.append(pipe.prove(times))
+    launches = ctx.launch_count - launches0
+    sampler.stop()
+    ms = sum(walls) / len(walls)
+    line = {"metric": "e2e prove data path ms (%s)" % pipe.describe(), "value": ms, "unit": "ms", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "prove() data path, BASELINE.json configs[%d]: %s" % (3 if kind == "ecc" else 2, pipe.describe()),
+                       "timing": "host wall clock per proof (the stages synchronise between each other); stage figures are CUDA events",
+                       "parity_preflight": "2^8-row instance of the same gate set: quotient values at sampled points == CPU oracle",
+                       "out_of_scope": "circuit building, witness generation, the per-circuit constants_sigmas commit"},
+            "stages_ms": {k: sum(times[k]) / len(times[k]) for k in STAGES if k in times},
+            "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "note": "the witness is generated on the device in this flow (no host copy on the path); proof bytes are read back inside the FRI call"},
+            "gpu_launches": launches, "clocks": sampler.summary()}
+    print(json.dumps(line), flush=True)
+    pipe.close()
+    ctx.close()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -534,6 +597,9 @@ def main():
                              "--master-addr 127.0.0.1 --master-port 29501 bench.py --gpus %d ..." % (args.gpus, args.gpus, args.gpus))
     if args.impl == "reference":
         run_reference(args, rank)
+    elif args.workload != "commit":
+        if rank == 0:
+            run_prove(args)
     else:
         run_b200(args, rank, world, local_rank)
 

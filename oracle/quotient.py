@@ -583,9 +583,20 @@ def root_of_unity(k):
     return b
 
 
-def compute_quotient_values(circ, wires_rows, zs_pp_rows, consts_sigmas_rows, pih, betas, gammas, alphas):
+def quotient_point_rows(circ, i):
+    """Leaf indices (row of x_i, row of g * x_i's `next` point) that point i of the quotient domain reads (prover.rs:923-943)."""
+    n_log, qdb, rb = circ.degree_bits, circ.quotient_degree_bits, circ.rate_bits
+    lde_size, lde_bits = 1 << (n_log + qdb), n_log + rb
+    step, next_step = 1 << (rb - qdb), 1 << qdb
+    rev = lambda v: int(format(v, "0%db" % lde_bits)[::-1], 2) if lde_bits else 0
+    return rev(i * step), rev(((i + next_step) % lde_size) * step)
+
+
+def compute_quotient_values(circ, wires_rows, zs_pp_rows, consts_sigmas_rows, pih, betas, gammas, alphas, points=None):
     """The loop of prover.rs:884-999: rows are the three batches' LDE leaves (leaf order, as the commit produces
-    them); returns quotient_values[i][challenge] for i over the 2^(degree_bits + quotient_degree_bits) points."""
+    them); returns quotient_values[i][challenge] for i over the 2^(degree_bits + quotient_degree_bits) points -- or only
+    for the listed `points` (the row containers then only need the rows quotient_point_rows() names: full-size parity on a
+    sample, tests/test_gpu_configs.py)."""
     n_log, qdb, rb = circ.degree_bits, circ.quotient_degree_bits, circ.rate_bits
     lde_size = 1 << (n_log + qdb)
     step, next_step = 1 << (rb - qdb), 1 << qdb
@@ -603,10 +614,8 @@ def compute_quotient_values(circ, wires_rows, zs_pp_rows, consts_sigmas_rows, pi
     zh_inv = [inv(z) for z in zh]
     nc, nr, md, npp = circ.num_challenges, circ.num_routed_wires, circ.quotient_degree_factor, circ.num_partial_products
     out = []
-    x_pow = 1
-    for i in range(lde_size):
-        x = g * x_pow % P
-        x_pow = x_pow * w % P
+    for i in (range(lde_size) if points is None else points):
+        x = g * pow(w, i, P) % P
         row = rev(i * step)
         row_next = rev(((i + next_step) % lde_size) * step)
         cs = [int(t) for t in consts_sigmas_rows[row]]
