@@ -1369,6 +1369,7 @@ static int quotient_impl(p2b_ctx* c, const p2b_circuit* circ, const u64* d_wires
   const u64 lde_size = (u64)1 << lde_log;
   quotient::GateDesc* d_gates = nullptr;
   u64 *d_kis = nullptr, *d_alphas = nullptr, *d_apows = nullptr, *d_vals = nullptr;
+  u32* d_work = nullptr;
   auto body = [&]() -> int {
     CUDA_TRY(cudaMallocAsync(&d_gates, (gates.size() ? gates.size() : 1) * sizeof(quotient::GateDesc), st));
     if (!gates.empty()) CUDA_TRY(cudaMemcpyAsync(d_gates, gates.data(), gates.size() * sizeof(quotient::GateDesc), cudaMemcpyHostToDevice, st));
@@ -1393,18 +1394,70 @@ static int quotient_impl(p2b_ctx* c, const p2b_circuit* circ, const u64* d_wires
     p.out_values = vals;
     p.out_rows = d_rows_out;
     {
-#ifndef P2B_QUOT_PPT
-#define P2B_QUOT_PPT 1
-#endif
-      constexpr int PPT = P2B_QUOT_PPT;  // points per thread (quotient.cuh: eval_batch)
-      constexpr unsigned BD = P2B_QUOT_BLOCK;
-      const unsigned blocks = (unsigned)((lde_size + BD * PPT - 1) / (BD * PPT));
-      const size_t smem = (size_t)nc * PPT * BD * sizeof(u64);
+      // tile geometry: the most point warps per CTA whose staged rows fit the opt-in shared memory
+      quotient::TileGeom tg{};
+      tg.nw = p.num_wires;
+      tg.ncs = p.num_constants + p.num_routed;
+      tg.nzs = nc * (1 + p.num_partial_products);
+      tg.ws = quotient::TileGeom::odd_stride(tg.nw);
+      tg.css = quotient::TileGeom::odd_stride(tg.ncs);
+      tg.zss = quotient::TileGeom::odd_stride(tg.nzs);
+      tg.tw = 0;
+      for (u32 tw : {6u, 4u, 3u, 2u, 1u}) {
+        tg.tw = tw;
+        if (tg.words() * sizeof(u64) + 3 * 192 * sizeof(void*) + 1024 <= c->smem_optin) break;
+        tg.tw = 0;
+      }
+      if (!tg.tw) return fail(P2B_ERR_UNSUPPORTED, "circuit rows (%u + %u + %u words) do not fit shared memory", tg.nw, tg.ncs, tg.nzs);
+      // work items (every non-trivial gate + the permutation argument) dealt to the 12 / tw groups: longest first, always to
+      // the least loaded group (LPT) over the instruction-count model of quotient::work_item_cost
+      const u32 G = tg.groups();
+      std::vector<std::pair<u64, u32>> items;
+      items.emplace_back(quotient::work_item_cost(p, nullptr), quotient::WORK_PERMUTATION);
+      for (u32 i = 0; i < gates.size(); i++)
+        if (gates[i].type != quotient::G_NOOP) items.emplace_back(quotient::work_item_cost(p, &gates[i]), i);
+      std::sort(items.begin(), items.end(), [](const std::pair<u64, u32>& a, const std::pair<u64, u32>& b2) { return a.first > b2.first; });
+      std::vector<std::vector<u32>> per_group(G);
+      std::vector<u64> load(G, 0);
+      for (auto& it : items) {
+        u32 best = 0;
+        for (u32 g2 = 1; g2 < G; g2++)
+          if (load[g2] < load[best]) best = g2;
+        per_group[best].push_back(it.second);
+        load[best] += it.first;
+      }
+      std::vector<u32> flat, begin(G + 1, 0);
+      for (u32 g2 = 0; g2 < G; g2++) {
+        begin[g2] = (u32)flat.size();
+        flat.insert(flat.end(), per_group[g2].begin(), per_group[g2].end());
+      }
+      begin[G] = (u32)flat.size();
+      CUDA_TRY(cudaMallocAsync(&d_work, (flat.size() + begin.size() + 1) * sizeof(u32), st));
+      CUDA_TRY(cudaMemcpyAsync(d_work, flat.data(), flat.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(d_work + flat.size(), begin.data(), begin.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaStreamSynchronize(st));   // flat / begin go out of scope
+      const u32* d_begin = d_work + flat.size();
+      const u64 matrix_rows = (u64)1 << (circ->degree_bits + circ->rate_bits);
+      const unsigned blocks = (unsigned)((lde_size + tg.points() - 1) / tg.points());
+      const size_t smem = tg.words() * sizeof(u64);
+      constexpr unsigned BD = quotient::QUOT_WARPS * 32;
       switch (nc) {
-        case 1: quotient::quotient_values_kernel<1, PPT><<<blocks, BD, smem, st>>>(p); break;
-        case 2: quotient::quotient_values_kernel<2, PPT><<<blocks, BD, smem, st>>>(p); break;
-        case 3: quotient::quotient_values_kernel<3, PPT><<<blocks, BD, smem, st>>>(p); break;
-        default: quotient::quotient_values_kernel<4, PPT><<<blocks, BD, smem, st>>>(p); break;
+        case 1:
+          P2B_TRY(opt_in_smem(quotient::quotient_values_kernel<1>, smem));
+          quotient::quotient_values_kernel<1><<<blocks, BD, smem, st>>>(p, tg, d_work, d_begin, matrix_rows);
+          break;
+        case 2:
+          P2B_TRY(opt_in_smem(quotient::quotient_values_kernel<2>, smem));
+          quotient::quotient_values_kernel<2><<<blocks, BD, smem, st>>>(p, tg, d_work, d_begin, matrix_rows);
+          break;
+        case 3:
+          P2B_TRY(opt_in_smem(quotient::quotient_values_kernel<3>, smem));
+          quotient::quotient_values_kernel<3><<<blocks, BD, smem, st>>>(p, tg, d_work, d_begin, matrix_rows);
+          break;
+        default:
+          P2B_TRY(opt_in_smem(quotient::quotient_values_kernel<4>, smem));
+          quotient::quotient_values_kernel<4><<<blocks, BD, smem, st>>>(p, tg, d_work, d_begin, matrix_rows);
+          break;
       }
     }
     c->launches++;
@@ -1426,7 +1479,7 @@ static int quotient_impl(p2b_ctx* c, const p2b_circuit* circ, const u64* d_wires
     return P2B_OK;
   };
   int rc = body();
-  for (void* ptr : {(void*)d_gates, (void*)d_kis, (void*)d_alphas, (void*)d_apows, (void*)d_vals})
+  for (void* ptr : {(void*)d_gates, (void*)d_kis, (void*)d_alphas, (void*)d_apows, (void*)d_vals, (void*)d_work})
     if (ptr) cudaFreeAsync(ptr, st);
   return rc;
 }

@@ -130,8 +130,8 @@ __device__ __forceinline__ u64 fsub(u64 a, u64 b) { return gl::sub(a, b); }
 __device__ __forceinline__ u64 fadd(u64 a, u64 b) { return gl::add(a, b); }
 
 // ---- gates (wires: W[k], constants after the selector prefix: K[k]) ----------------------------------------------
-#define W(k) __ldg(w + (k))
-#define K(k) __ldg(kc + (k))
+#define W(k) (w[(k)])
+#define K(k) (kc[(k)])
 
 template <class E>
 __device__ __forceinline__ void eval_constant(const GateDesc& g, const u64* w, const u64* kc, E& e) {  // constant.rs:150-158
@@ -420,18 +420,25 @@ __device__ __forceinline__ void eval_poseidon(const u64* w, E& e) {
 #pragma unroll
   for (int i = 8; i < 12; i++) s[i] = W(i);
   using namespace poseidon;
+  // The gate's constraints are stated in the reference through the fast partial-round form (gates/poseidon.rs:485-564); the
+  // quantities they constrain -- the value entering every S-box, and the output state -- are the same in the naive round
+  // structure (the fast form only changes the basis of lanes 1..11 between partial rounds, lane 0 is fixed by every one of
+  // its matrices), so the evaluation walks the 30 naive rounds with the multiplier-free FP64 MDS layer of poseidon.cuh:
+  // after mds_naive(.., constants of round r+1) the state IS the S-box input of round r+1.  Pinned against the reference's
+  // own device evaluator on arbitrary rows (tests/test_ref_cuda_crosscheck.py).
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl::add_canonical(s[i], C.rc[i]);
 #pragma unroll 1
-  for (int r = 0; r < 4; r++) {
-    if (r != 0) {
-      // state (constants of this round already folded in by the previous MDS) must equal the S-box input wires
+  for (int r = 0; r < 30; r++) {
+    const bool full = r < 4 || r >= 26;
+    if (full && r != 0) {
+      const u32 base = r < 4 ? FULL0 + 12 * (r - 1) : FULL1 + 12 * (r - 26);
 #pragma unroll 1
       for (int g4 = 0; g4 < 3; g4++) {
-        // processed through the same 3 x 4 rotation as sbox_layer to keep the register array statically indexed
+        // the state must equal the S-box input wires; processed through a 3 x 4 rotation to keep the register array
+        // statically indexed
         u64 t0 = s[0], t1 = s[1], t2 = s[2], t3 = s[3];
-        u64 v0 = W(FULL0 + 12 * (r - 1) + 4 * g4 + 0), v1 = W(FULL0 + 12 * (r - 1) + 4 * g4 + 1);
-        u64 v2 = W(FULL0 + 12 * (r - 1) + 4 * g4 + 2), v3 = W(FULL0 + 12 * (r - 1) + 4 * g4 + 3);
+        u64 v0 = W(base + 4 * g4 + 0), v1 = W(base + 4 * g4 + 1), v2 = W(base + 4 * g4 + 2), v3 = W(base + 4 * g4 + 3);
         e.emit(fsub(t0, v0));
         e.emit(fsub(t1, v1));
         e.emit(fsub(t2, v2));
@@ -441,36 +448,14 @@ __device__ __forceinline__ void eval_poseidon(const u64* w, E& e) {
         s[8] = v0; s[9] = v1; s[10] = v2; s[11] = v3;
       }
     }
-    sbox_layer_rolled(s, e.mode);
-    mds_layer(s, &C.post[12 * r]);  // + constants of the next full round / first partial constants after r = 3
-  }
-  partial_layer_init(s, e.mode);
-#pragma unroll 1
-  for (int r = 0; r < 22; r++) {
-    u64 sbox_in = W(PARTIAL + r);
-    e.emit(fsub(s[0], sbox_in));
-    u64 s0 = gl::add_canonical(sbox(sbox_in, e.mode), C.partial_rc[r]);  // partial_rc[21] == 0 (poseidon.rs:544 adds nothing)
-    partial_layer_fast(s, s0, r, e.mode);
-  }
-#pragma unroll
-  for (int i = 0; i < 12; i++) s[i] = gl::add_canonical(s[i], C.rc[12 * 26 + i]);
-#pragma unroll 1
-  for (int r = 0; r < 4; r++) {
-#pragma unroll 1
-    for (int g4 = 0; g4 < 3; g4++) {
-      u64 t0 = s[0], t1 = s[1], t2 = s[2], t3 = s[3];
-      u64 v0 = W(FULL1 + 12 * r + 4 * g4 + 0), v1 = W(FULL1 + 12 * r + 4 * g4 + 1);
-      u64 v2 = W(FULL1 + 12 * r + 4 * g4 + 2), v3 = W(FULL1 + 12 * r + 4 * g4 + 3);
-      e.emit(fsub(t0, v0));
-      e.emit(fsub(t1, v1));
-      e.emit(fsub(t2, v2));
-      e.emit(fsub(t3, v3));
-#pragma unroll
-      for (int i = 0; i < 8; i++) s[i] = s[i + 4];
-      s[8] = v0; s[9] = v1; s[10] = v2; s[11] = v3;
+    if (full) {
+      sbox_layer_rolled(s, e.mode);
+    } else {
+      const u64 sbox_in = W(PARTIAL + (r - 4));
+      e.emit(fsub(s[0], sbox_in));
+      s[0] = sbox(sbox_in, e.mode);
     }
-    sbox_layer_rolled(s, e.mode);
-    mds_layer(s, &C.post[12 * (4 + r)]);
+    mds_naive(s, C.rc_d + 24 * (r + 1), e.mode);
   }
 #pragma unroll 1
   for (int g4 = 0; g4 < 3; g4++) {
@@ -490,37 +475,29 @@ __device__ __forceinline__ void eval_poseidon(const u64* w, E& e) {
 // field inverse by Fermat (the reference uses a binary GCD, field/src/inversion.rs; the value is the same)
 __device__ __forceinline__ u64 finv(u64 a) { return gl::pow(a, gl::P - 2); }
 
-// One thread evaluates PPT points, gate by gate: for every gate the PPT points run through the same evaluator code
-// back to back, so the instruction stream of a gate (the kernel is ~300 KB of SASS) is fetched once per PPT points instead
-// of once per point -- instruction-cache misses were the top stall (profiles/r01_quotient.md).  The per-point partial
-// sums live in shared memory: acc[(c * PPT + k) * blockDim + tid].
+// ---- the kernel ----------------------------------------------------------------------------------------------------
+// A CTA of 12 warps owns a TILE of TW * 32 consecutive points of the quotient domain (TW = 1, 2, 3, 4 or 6 "point warps").
+// Phase 1 stages the three leaf rows of every point of the tile (+ the next row's Z values) into shared memory with
+// cp.async.bulk (one TMA bulk copy per row and matrix, completion on an mbarrier) -- a point's rows are contiguous 1-3 KB
+// segments of the leaf-major matrices the commit kernels wrote, scattered by the bit reversal, which is exactly what a
+// bulk copy wants and what per-thread loads are worst at (round 1: 12 warps per SM stalled on long-scoreboard loads 74% of
+// the time, rows re-read from DRAM for every gate).  Phase 2 splits the circuit's work items -- every gate instance and the
+// permutation argument -- into 12 / TW groups of similar cost (host-side LPT over an instruction-count model); warp
+// (group, point warp) evaluates its group's items for its 32 points out of shared memory, so all lanes of a warp run the
+// same evaluator (no divergence) and nothing waits on global memory.  Phase 3 adds the groups' partial sums, multiplies by
+// 1 / Z_H and writes the values.  Every row is read from HBM exactly once.
 struct PointRows {
   const u64 *w, *cs, *zp, *zn;
   u64 x;
 };
-__device__ __forceinline__ PointRows point_rows(const Params& p, const u64 i, const u64 lde_size, bool with_x) {
-  const u32 lde_bits = p.degree_bits + p.rate_bits;
-  const u32 step_log = p.rate_bits - p.qdb;
-  const u64 row = lde_bits ? (__brevll(i << step_log) >> (64 - lde_bits)) : 0;
-  const u64 i_next = (i + ((u64)1 << p.qdb)) & (lde_size - 1);
-  const u64 row_next = lde_bits ? (__brevll(i_next << step_log) >> (64 - lde_bits)) : 0;
-  PointRows r;
-  r.w = p.wires + row * p.wires_stride;
-  r.cs = p.cs + row * p.cs_stride;
-  r.zp = p.zs_pp + row * p.zs_stride;
-  r.zn = p.zs_pp + row_next * p.zs_stride;
-  r.x = with_x ? gl::mul(7, gl::pow(p.w, i)) : 0;  // shifted_x = coset_shift * w^i (prover.rs:907)
-  return r;
-}
 
 // vanishing_z_1_terms and partial-product checks (vanishing_poly.rs:160-205) of one point.
 // reduce_with_powers_multi reduces ONE term list [z1 terms of every challenge | pp checks of every challenge |
 // gate constraints] with each alpha, so the terms produced for challenge tc enter every challenge c's sum.
 template <class M, int NC>
-__device__ __forceinline__ void eval_permutation_terms(const Params& p, const u64 i, const u64 lde_size, M& mode, u64 (&acc)[NC]) {
-  const PointRows r = point_rows(p, i, lde_size, true);
+__device__ __forceinline__ void eval_permutation_terms(const Params& p, const PointRows& r, const u64 i, M& mode, u64 (&acc)[NC]) {
   const u64 *w = r.w, *cs = r.cs, *zp = r.zp, *zn = r.zn;
-  const u64 x = r.x;
+  const u64 x = gl::mul(7, gl::pow(p.w, i));  // shifted_x = coset_shift * w^i (prover.rs:907)
   const u32 nr = p.num_routed, npp = p.num_partial_products, md = p.max_degree;
   const u32 rate_mask = (1u << p.qdb) - 1;
   auto fm = [&](u64 a, u64 b) { return gl::mul(a, b, mode); };
@@ -532,7 +509,7 @@ __device__ __forceinline__ void eval_permutation_terms(const Params& p, const u6
   const u32 chunks = npp + 1;
 #pragma unroll 1
   for (u32 tc = 0; tc < (u32)NC; tc++) {
-    const u64 z_x = __ldg(zp + tc), z_gx = __ldg(zn + tc);
+    const u64 z_x = zp[tc], z_gx = zn[tc];
     const u64 t_z1 = fm(l0, gl::sub(z_x, 1));
 #pragma unroll
     for (int c = 0; c < NC; c++) acc[c] = fma(t_z1, __ldg(p.alpha_pows + (u64)c * p.num_terms + tc), acc[c]);
@@ -543,11 +520,11 @@ __device__ __forceinline__ void eval_permutation_terms(const Params& p, const u6
       u64 num = 1, den = 1;
       const u32 j1 = min(nr, (ch + 1) * md);
       for (u32 j = ch * md; j < j1; j++) {
-        const u64 wv = __ldg(w + j);
-        num = fm(num, gl::add(gl::add(wv, fm(bx, __ldg(p.k_is + j))), gamma));                    // :175-181
-        den = fm(den, gl::add(gl::add(wv, fm(beta, __ldg(cs + p.num_constants + j))), gamma));     // :182-186
+        const u64 wv = w[j];
+        num = fm(num, gl::add(gl::add(wv, fm(bx, __ldg(p.k_is + j))), gamma));               // :175-181
+        den = fm(den, gl::add(gl::add(wv, fm(beta, cs[p.num_constants + j])), gamma));       // :182-186
       }
-      const u64 next = ch + 1 < chunks ? __ldg(zp + NC + tc * npp + ch) : z_gx;
+      const u64 next = ch + 1 < chunks ? zp[NC + tc * npp + ch] : z_gx;
       const u64 term = gl::sub(fm(prev, num), fm(next, den));  // partial_products.rs:70-75
 #pragma unroll
       for (int c = 0; c < NC; c++)
@@ -559,14 +536,13 @@ __device__ __forceinline__ void eval_permutation_terms(const Params& p, const u6
 
 // filter_g * sum_j alpha_c^(gate_base + j) c_{g,j} of one gate at one point (vanishing_poly.rs:267-306)
 template <class M, int NC>
-__device__ __forceinline__ void eval_gate_terms(const Params& p, const GateDesc& g, const u32 gi, const u64 i, const u64 lde_size,
-                                                M& mode, u64 (&out)[NC]) {
-  const PointRows r = point_rows(p, i, lde_size, false);
+__device__ __forceinline__ void eval_gate_terms(const Params& p, const GateDesc& g, const u32 gi, const PointRows& r, M& mode,
+                                                u64 (&out)[NC]) {
   const u64 *w = r.w, *cs = r.cs;
   const u64* kc = cs + p.num_selectors;  // vars.remove_prefix(num_selectors), gate.rs:138
   auto fm = [&](u64 a, u64 b) { return gl::mul(a, b, mode); };
   // compute_filter (gate.rs:261-268)
-  const u64 s = __ldg(cs + g.selector_index);
+  const u64 s = cs[g.selector_index];
   u64 filter = 1;
   for (u32 k = g.group_start; k < g.group_end; k++)
     if (k != gi) filter = fm(filter, gl::sub((u64)k, s));
@@ -600,70 +576,190 @@ __device__ __forceinline__ void eval_gate_terms(const Params& p, const GateDesc&
   for (int c = 0; c < NC; c++) out[c] = fm(filter, e.result(c));
 }
 
-// the PPT points of this thread: i_k = first + k * blockDim.x
-template <class M, int NC, int PPT>
-__device__ __forceinline__ void eval_batch(const Params& p, const u64 first, const u64 lde_size, M& mode, u64* __restrict__ sh) {
-  const u32 bd = blockDim.x;
-#pragma unroll 1
-  for (int k = 0; k < PPT; k++) {
-    const u64 i = first + (u64)k * bd;
-    if (i >= lde_size) break;
-    u64 a[NC];
-    eval_permutation_terms(p, i, lde_size, mode, a);
-#pragma unroll
-    for (int c = 0; c < NC; c++) sh[(c * PPT + k) * bd] = a[c];
+static constexpr u32 QUOT_WARPS = 12;           // CTA = 384 threads
+static constexpr u32 WORK_PERMUTATION = 0xFFFFFFFFu;  // work item that is not a gate: the permutation argument's terms
+
+// Shared-memory geometry of a tile (u64 words).  A row slot holds [align pad <= 1][lead <= 1][row][tail pad <= 1]: the bulk
+// copy's destination must be 16-byte aligned and it fetches the 16-byte aligned span around the (8-byte aligned) row.  Slot
+// strides are ODD so that the 32 points of a warp reading the same wire fall into different bank pairs.
+struct TileGeom {
+  u32 tw;                       // point warps per tile
+  u32 ws, css, zss;             // slot strides of the three staged matrices (odd, >= words + 3)
+  u32 nw, ncs, nzs;             // words copied per row
+  __host__ __device__ u32 points() const { return tw * 32; }
+  __host__ __device__ u32 groups() const { return QUOT_WARPS / tw; }
+  __host__ __device__ size_t words() const {
+    return 2 + (size_t)points() * (ws + css + zss + MAX_CHALLENGES) + (size_t)groups() * MAX_CHALLENGES * points();
   }
-#pragma unroll 1
-  for (u32 gi = 0; gi < p.num_gates; gi++) {
-    const GateDesc g = p.gates[gi];
-    if (g.type == G_NOOP) continue;
-#pragma unroll 1
-    for (int k = 0; k < PPT; k++) {
-      const u64 i = first + (u64)k * bd;
-      if (i >= lde_size) break;
-      u64 t[NC];
-      eval_gate_terms(p, g, gi, i, lde_size, mode, t);
-#pragma unroll
-      for (int c = 0; c < NC; c++) sh[(c * PPT + k) * bd] = gl::add(sh[(c * PPT + k) * bd], t[c]);
-    }
-    // keep the CTA's warps on the same gate: they then share the instruction-cache lines of that gate's evaluator
-    __syncthreads();
-  }
+  __host__ static u32 odd_stride(u32 words) { return (words + 3) | 1; }
+};
+
+// cp.async.bulk global -> shared of `bytes` (multiple of 16) from a 16-byte aligned source, completing on `mbar`
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, u32 bytes, u64* mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (u32)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"((u32)__cvta_generic_to_shared(mbar))
+               : "memory");
 }
 
-#ifndef P2B_QUOT_BLOCK
-#define P2B_QUOT_BLOCK 384
-#endif
-template <int NC, int PPT>
-__global__ void __launch_bounds__(P2B_QUOT_BLOCK) quotient_values_kernel(Params p) {
-  extern __shared__ u64 qsh[];  // [NC][PPT][blockDim]
+// Stages one row (nwords u64 at src, 8-byte aligned) into the slot at `slot`: the bulk copy fetches the enclosing 16-byte
+// aligned span [src - lead, ...) into the slot's first 16-byte aligned word; *row_out points at the row inside the slot.
+__device__ __forceinline__ void stage_row(u64* slot, const u64* src, u32 nwords, u64* mbar, u64** row_out) {
+  u64* dst = slot + ((((u64)__cvta_generic_to_shared(slot)) >> 3) & 1);   // 16-byte aligned
+  const u32 lead = (u32)((((u64)src) >> 3) & 1);                          // 1 if the row starts in the upper half of a 16-byte unit
+  const u32 bytes = ((lead + nwords + 1) & ~1u) * 8;
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(mbar)), "r"(bytes) : "memory");
+  bulk_load(dst, src - lead, bytes, mbar);
+  *row_out = dst + lead;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(QUOT_WARPS * 32) quotient_values_kernel(Params p, TileGeom tg, const u32* __restrict__ work_items,
+                                                                          const u32* __restrict__ group_begin, u64 matrix_rows) {
+  extern __shared__ __align__(16) u64 qsh[];
+  const u32 TP = tg.points(), G = tg.groups();
+  // layout: [mbar (2 words)] [wires TP x ws] [cs TP x css] [zs TP x zss] [zn TP x MAX_CH] [part G x NC x TP]
+  u64* mbar = qsh;
+  u64* sw = qsh + 2;
+  u64* scs = sw + (size_t)TP * tg.ws;
+  u64* szs = scs + (size_t)TP * tg.css;
+  u64* szn = szs + (size_t)TP * tg.zss;
+  u64* part = szn + (size_t)TP * MAX_CHALLENGES;
+  __shared__ const u64* row_w[QUOT_WARPS * 32 / 2];   // >= TP (TP <= 192)
+  __shared__ const u64* row_cs[QUOT_WARPS * 32 / 2];
+  __shared__ const u64* row_zs[QUOT_WARPS * 32 / 2];
   const u64 lde_size = (u64)1 << (p.degree_bits + p.qdb);
-  const u64 first = (u64)blockIdx.x * blockDim.x * PPT + threadIdx.x;  // may lie beyond the domain: such threads only keep the barriers
-  u64* sh = qsh + threadIdx.x;
+  const u64 tile_first = (u64)blockIdx.x * TP;
+  const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const u32 lde_bits = p.degree_bits + p.rate_bits, step_log = p.rate_bits - p.qdb;
+
+  // ---- phase 1: stage the rows ----
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(mbar)), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid < TP) {
+    u64 i = tile_first + tid;
+    if (i >= lde_size) i = lde_size - 1;  // tail slots recompute the last point; their results are not stored
+    const u64 row = lde_bits ? (__brevll(i << step_log) >> (64 - lde_bits)) : 0;
+    const u64 i_next = (i + ((u64)1 << p.qdb)) & (lde_size - 1);
+    const u64 row_next = lde_bits ? (__brevll(i_next << step_log) >> (64 - lde_bits)) : 0;
+    u64 *rw, *rc, *rz;
+    // the last row of a matrix may not be followed by a readable word: it is copied with ordinary loads
+    const bool last = row + 1 == matrix_rows;
+    if (!last) {
+      stage_row(sw + (size_t)tid * tg.ws, p.wires + row * p.wires_stride, tg.nw, mbar, &rw);
+      stage_row(scs + (size_t)tid * tg.css, p.cs + row * p.cs_stride, tg.ncs, mbar, &rc);
+      stage_row(szs + (size_t)tid * tg.zss, p.zs_pp + row * p.zs_stride, tg.nzs, mbar, &rz);
+    } else {
+      rw = sw + (size_t)tid * tg.ws;
+      rc = scs + (size_t)tid * tg.css;
+      rz = szs + (size_t)tid * tg.zss;
+      for (u32 k = 0; k < tg.nw; k++) rw[k] = p.wires[row * p.wires_stride + k];
+      for (u32 k = 0; k < tg.ncs; k++) rc[k] = p.cs[row * p.cs_stride + k];
+      for (u32 k = 0; k < tg.nzs; k++) rz[k] = p.zs_pp[row * p.zs_stride + k];
+    }
+    row_w[tid] = rw;
+    row_cs[tid] = rc;
+    row_zs[tid] = rz;
+    for (u32 c = 0; c < (u32)NC; c++) szn[(size_t)tid * MAX_CHALLENGES + c] = __ldg(p.zs_pp + row_next * p.zs_stride + c);
+  }
+  __syncthreads();   // all expect_tx are registered before the single arrival
+  if (tid == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((u32)__cvta_generic_to_shared(mbar)) : "memory");
+  {
+    u32 done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred q; mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2; selp.u32 %0, 1, 0, q; }"
+                   : "=r"(done)
+                   : "r"((u32)__cvta_generic_to_shared(mbar)), "r"(0)
+                   : "memory");
+  }
+  __syncthreads();
+
+  // ---- phase 2: warp (group, point warp) evaluates its group's work items for its 32 points ----
+  const u32 group = wid / tg.tw, slot = (wid % tg.tw) * 32 + lane;
+  const u64 i = min(tile_first + slot, lde_size - 1);
+  PointRows r;
+  r.w = row_w[slot];
+  r.cs = row_cs[slot];
+  r.zp = row_zs[slot];
+  r.zn = szn + (size_t)slot * MAX_CHALLENGES;
+  r.x = 0;
+  const u32 it0 = group_begin[group], it1 = group_begin[group + 1];
+  auto run = [&](auto& mode) {
+    u64 acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) acc[c] = 0;
+#pragma unroll 1
+    for (u32 it = it0; it < it1; it++) {
+      const u32 item = work_items[it];
+      u64 t[NC];
+      if (item == WORK_PERMUTATION) {
+        eval_permutation_terms(p, r, i, mode, t);
+      } else {
+        const GateDesc g = p.gates[item];
+        eval_gate_terms(p, g, item, r, mode, t);
+      }
+#pragma unroll
+      for (int c = 0; c < NC; c++) acc[c] = gl::add(acc[c], t[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < NC; c++) part[((size_t)group * NC + c) * TP + slot] = acc[c];
+  };
 #ifndef P2B_EXACT_ONLY
   gl::Optimistic fast;
-  eval_batch<gl::Optimistic, NC, PPT>(p, first, lde_size, fast, sh);
-  // an optimistic reduction hit its rare case somewhere in this CTA's points: redo them exactly (CTA-wide decision: the
-  // evaluation contains barriers)
+  run(fast);
+  // an optimistic reduction hit its rare case somewhere in this CTA's points: redo the tile exactly
   if (__syncthreads_or(fast.rare))
 #endif
   {
     gl::Exact exact;
-    eval_batch<gl::Exact, NC, PPT>(p, first, lde_size, exact, sh);
+    run(exact);
   }
-  // ---- divide by Z_H (prover.rs:985-991) ----
-#pragma unroll 1
-  for (int k = 0; k < PPT; k++) {
-    const u64 i = first + (u64)k * blockDim.x;
-    if (i >= lde_size) break;
-    const u64 zi = p.zh_inv[i & ((1u << p.qdb) - 1)];
+  __syncthreads();
+  // ---- phase 3: sum the groups, divide by Z_H (prover.rs:985-991) ----
+  if (tid < TP && tile_first + tid < lde_size) {
+    const u64 pi = tile_first + tid;
+    const u64 zi = p.zh_inv[pi & ((1u << p.qdb) - 1)];
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-      const u64 v = gl::canon(gl::mul(sh[(c * PPT + k) * blockDim.x], zi));
-      p.out_values[(u64)c * lde_size + i] = v;
-      if (p.out_rows) p.out_rows[i * NC + c] = v;
+      u64 v = 0;
+      for (u32 g2 = 0; g2 < G; g2++) v = gl::add(v, part[((size_t)g2 * NC + c) * TP + tid]);
+      v = gl::canon(gl::mul(v, zi));
+      p.out_values[(u64)c * lde_size + pi] = v;
+      if (p.out_rows) p.out_rows[pi * NC + c] = v;
     }
   }
+}
+
+// host: rough thread-instruction cost of one work item (only the RATIOS matter: they balance the groups)
+inline u64 work_item_cost(const Params& p, const GateDesc* g) {
+  const u64 nc = p.num_challenges, emit = 12 * nc + 6;
+  if (!g) return (u64)p.num_routed * nc * 70 + (u64)(p.num_partial_products + 2) * nc * (emit + 40) + 1500;
+  const u64 k = gate_num_constraints(*g);
+  u64 extra = 0;
+  switch (g->type) {
+    case G_ARITHMETIC: extra = (u64)g->p0 * 50; break;
+    case G_BASE_SUM: extra = (u64)g->p0 * (20 + 14 * g->p1); break;
+    case G_POSEIDON: extra = 17000; break;
+    case G_RANDOM_ACCESS: extra = (u64)g->p1 * ((1u << g->p0) * 25 + g->p0 * 30); break;
+    case G_U32_ARITHMETIC: extra = (u64)g->p0 * 36 * 45; break;
+    case G_U32_ADD_MANY: extra = (u64)g->p1 * 21 * 45; break;
+    case G_U32_RANGE_CHECK: extra = (u64)g->p0 * 17 * 45; break;
+    case G_U32_SUBTRACTION: extra = (u64)g->p0 * 19 * 45; break;
+    case G_COMPARISON: extra = k * 60; break;
+    case G_ARITHMETIC_EXT: extra = (u64)g->p0 * 130; break;
+    case G_MUL_EXT: extra = (u64)g->p0 * 90; break;
+    case G_REDUCING: extra = (u64)g->p0 * 70; break;
+    case G_REDUCING_EXT: extra = (u64)g->p0 * 110; break;
+    case G_EXPONENTIATION: extra = (u64)g->p0 * 45; break;
+    case G_POSEIDON_MDS: extra = 9000; break;
+    case G_HIGH_DEGREE_INTERPOLATION: extra = (u64)(1u << g->p0) * 400; break;
+    case G_LOW_DEGREE_INTERPOLATION: extra = (u64)(1u << g->p0) * 500; break;
+    default: break;
+  }
+  return k * emit + extra + 200;
 }
 
 // coefficients[i] *= shift_inv^i  (coset_ifft, field/src/polynomial/mod.rs:64-77)
