@@ -1409,34 +1409,19 @@ static int quotient_impl(p2b_ctx* c, const p2b_circuit* circ, const u64* d_wires
         tg.tw = 0;
       }
       if (!tg.tw) return fail(P2B_ERR_UNSUPPORTED, "circuit rows (%u + %u + %u words) do not fit shared memory", tg.nw, tg.ncs, tg.nzs);
-      // work items (every non-trivial gate + the permutation argument) dealt to the 12 / tw groups: longest first, always to
-      // the least loaded group (LPT) over the instruction-count model of quotient::work_item_cost
-      const u32 G = tg.groups();
+      // work items (every non-trivial gate + the permutation argument), longest first by the instruction-count model of
+      // quotient::work_item_cost: the kernel's warp groups pull them in this order
       std::vector<std::pair<u64, u32>> items;
       items.emplace_back(quotient::work_item_cost(p, nullptr), quotient::WORK_PERMUTATION);
       for (u32 i = 0; i < gates.size(); i++)
         if (gates[i].type != quotient::G_NOOP) items.emplace_back(quotient::work_item_cost(p, &gates[i]), i);
-      std::sort(items.begin(), items.end(), [](const std::pair<u64, u32>& a, const std::pair<u64, u32>& b2) { return a.first > b2.first; });
-      std::vector<std::vector<u32>> per_group(G);
-      std::vector<u64> load(G, 0);
-      for (auto& it : items) {
-        u32 best = 0;
-        for (u32 g2 = 1; g2 < G; g2++)
-          if (load[g2] < load[best]) best = g2;
-        per_group[best].push_back(it.second);
-        load[best] += it.first;
-      }
-      std::vector<u32> flat, begin(G + 1, 0);
-      for (u32 g2 = 0; g2 < G; g2++) {
-        begin[g2] = (u32)flat.size();
-        flat.insert(flat.end(), per_group[g2].begin(), per_group[g2].end());
-      }
-      begin[G] = (u32)flat.size();
-      CUDA_TRY(cudaMallocAsync(&d_work, (flat.size() + begin.size() + 1) * sizeof(u32), st));
+      std::stable_sort(items.begin(), items.end(), [](const std::pair<u64, u32>& a, const std::pair<u64, u32>& b2) { return a.first > b2.first; });
+      std::vector<u32> flat;
+      for (auto& it : items) flat.push_back(it.second);
+      CUDA_TRY(cudaMallocAsync(&d_work, flat.size() * sizeof(u32), st));
       CUDA_TRY(cudaMemcpyAsync(d_work, flat.data(), flat.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
-      CUDA_TRY(cudaMemcpyAsync(d_work + flat.size(), begin.data(), begin.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
-      CUDA_TRY(cudaStreamSynchronize(st));   // flat / begin go out of scope
-      const u32* d_begin = d_work + flat.size();
+      CUDA_TRY(cudaStreamSynchronize(st));   // flat goes out of scope
+      const u32 num_items = (u32)flat.size();
       const u64 matrix_rows = (u64)1 << (circ->degree_bits + circ->rate_bits);
       const unsigned blocks = (unsigned)((lde_size + tg.points() - 1) / tg.points());
       const size_t smem = tg.words() * sizeof(u64);
@@ -1444,19 +1429,19 @@ static int quotient_impl(p2b_ctx* c, const p2b_circuit* circ, const u64* d_wires
       switch (nc) {
         case 1:
           P2B_TRY(opt_in_smem(quotient::quotient_values_kernel<1>, smem));
-          quotient::quotient_values_kernel<1><<<blocks, BD, smem, st>>>(p, tg, d_work, d_begin, matrix_rows);
+          quotient::quotient_values_kernel<1><<<blocks, BD, smem, st>>>(p, tg, d_work, num_items, matrix_rows);
           break;
         case 2:
           P2B_TRY(opt_in_smem(quotient::quotient_values_kernel<2>, smem));
-          quotient::quotient_values_kernel<2><<<blocks, BD, smem, st>>>(p, tg, d_work, d_begin, matrix_rows);
+          quotient::quotient_values_kernel<2><<<blocks, BD, smem, st>>>(p, tg, d_work, num_items, matrix_rows);
           break;
         case 3:
           P2B_TRY(opt_in_smem(quotient::quotient_values_kernel<3>, smem));
-          quotient::quotient_values_kernel<3><<<blocks, BD, smem, st>>>(p, tg, d_work, d_begin, matrix_rows);
+          quotient::quotient_values_kernel<3><<<blocks, BD, smem, st>>>(p, tg, d_work, num_items, matrix_rows);
           break;
         default:
           P2B_TRY(opt_in_smem(quotient::quotient_values_kernel<4>, smem));
-          quotient::quotient_values_kernel<4><<<blocks, BD, smem, st>>>(p, tg, d_work, d_begin, matrix_rows);
+          quotient::quotient_values_kernel<4><<<blocks, BD, smem, st>>>(p, tg, d_work, num_items, matrix_rows);
           break;
       }
     }

@@ -481,11 +481,13 @@ __device__ __forceinline__ u64 finv(u64 a) { return gl::pow(a, gl::P - 2); }
 // cp.async.bulk (one TMA bulk copy per row and matrix, completion on an mbarrier) -- a point's rows are contiguous 1-3 KB
 // segments of the leaf-major matrices the commit kernels wrote, scattered by the bit reversal, which is exactly what a
 // bulk copy wants and what per-thread loads are worst at (round 1: 12 warps per SM stalled on long-scoreboard loads 74% of
-// the time, rows re-read from DRAM for every gate).  Phase 2 splits the circuit's work items -- every gate instance and the
-// permutation argument -- into 12 / TW groups of similar cost (host-side LPT over an instruction-count model); warp
-// (group, point warp) evaluates its group's items for its 32 points out of shared memory, so all lanes of a warp run the
-// same evaluator (no divergence) and nothing waits on global memory.  Phase 3 adds the groups' partial sums, multiplies by
-// 1 / Z_H and writes the values.  Every row is read from HBM exactly once.
+// the time, rows re-read from DRAM for every gate).  Phase 2: the 12 warps form 12 / TW groups of TW warps (one per point
+// warp of the tile); a group pulls the next work item -- one gate instance or the permutation argument, ordered longest first
+// by a host-side instruction-count model -- from a shared-memory queue and its warps evaluate that item for their 32 points
+// each out of shared memory.  All lanes of a warp run the same evaluator (no divergence), the warps of a group share its
+// instruction-cache lines, nothing waits on global memory, and the greedy longest-first order keeps the groups busy to the
+// end whatever the model's errors (a static split left 2 stall cycles per issue at the final barrier).  Phase 3 adds the
+// groups' partial sums, multiplies by 1 / Z_H and writes the values.  Every row is read from HBM exactly once.
 struct PointRows {
   const u64 *w, *cs, *zp, *zn;
   u64 x;
@@ -589,7 +591,7 @@ struct TileGeom {
   __host__ __device__ u32 points() const { return tw * 32; }
   __host__ __device__ u32 groups() const { return QUOT_WARPS / tw; }
   __host__ __device__ size_t words() const {
-    return 2 + (size_t)points() * (ws + css + zss + MAX_CHALLENGES) + (size_t)groups() * MAX_CHALLENGES * points();
+    return 2 + 16 /* queue */ + (size_t)points() * (ws + css + zss + MAX_CHALLENGES) + (size_t)groups() * MAX_CHALLENGES * points();
   }
   __host__ static u32 odd_stride(u32 words) { return (words + 3) | 1; }
 };
@@ -615,12 +617,14 @@ __device__ __forceinline__ void stage_row(u64* slot, const u64* src, u32 nwords,
 
 template <int NC>
 __global__ void __launch_bounds__(QUOT_WARPS * 32) quotient_values_kernel(Params p, TileGeom tg, const u32* __restrict__ work_items,
-                                                                          const u32* __restrict__ group_begin, u64 matrix_rows) {
+                                                                          u32 num_items, u64 matrix_rows) {
   extern __shared__ __align__(16) u64 qsh[];
   const u32 TP = tg.points(), G = tg.groups();
-  // layout: [mbar (2 words)] [wires TP x ws] [cs TP x css] [zs TP x zss] [zn TP x MAX_CH] [part G x NC x TP]
+  // layout: [mbar (2 words)] [queue: counters (2 x u32), per-group item slots (2 x 12 x u32)] [wires TP x ws] [cs TP x css]
+  //         [zs TP x zss] [zn TP x MAX_CH] [part G x NC x TP]
   u64* mbar = qsh;
-  u64* sw = qsh + 2;
+  u32* queue = reinterpret_cast<u32*>(qsh + 2);   // [0], [1]: next item (optimistic pass, exact pass); [2 + 2g + parity]: group g's item
+  u64* sw = qsh + 2 + 16;
   u64* scs = sw + (size_t)TP * tg.ws;
   u64* szs = scs + (size_t)TP * tg.css;
   u64* szn = szs + (size_t)TP * tg.zss;
@@ -637,6 +641,8 @@ __global__ void __launch_bounds__(QUOT_WARPS * 32) quotient_values_kernel(Params
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((u32)__cvta_generic_to_shared(mbar)), "r"(1) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    queue[0] = 0;
+    queue[1] = 0;
   }
   __syncthreads();
   if (tid < TP) {
@@ -686,14 +692,20 @@ __global__ void __launch_bounds__(QUOT_WARPS * 32) quotient_values_kernel(Params
   r.zp = row_zs[slot];
   r.zn = szn + (size_t)slot * MAX_CHALLENGES;
   r.x = 0;
-  const u32 it0 = group_begin[group], it1 = group_begin[group + 1];
-  auto run = [&](auto& mode) {
+  const u32 pw = wid % tg.tw;
+  auto run = [&](auto& mode, u32* counter) {
     u64 acc[NC];
 #pragma unroll
     for (int c = 0; c < NC; c++) acc[c] = 0;
 #pragma unroll 1
-    for (u32 it = it0; it < it1; it++) {
-      const u32 item = work_items[it];
+    for (u32 it = 0;; it++) {
+      // the group's first warp takes the next item off the queue; a named barrier (one per group) publishes it
+      u32* slot_item = queue + 2 + 2 * group + (it & 1);
+      if (pw == 0 && lane == 0) *slot_item = atomicAdd(counter, 1u);
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "r"(tg.tw * 32) : "memory");
+      const u32 idx = *slot_item;
+      if (idx >= num_items) break;
+      const u32 item = work_items[idx];
       u64 t[NC];
       if (item == WORK_PERMUTATION) {
         eval_permutation_terms(p, r, i, mode, t);
@@ -709,13 +721,13 @@ __global__ void __launch_bounds__(QUOT_WARPS * 32) quotient_values_kernel(Params
   };
 #ifndef P2B_EXACT_ONLY
   gl::Optimistic fast;
-  run(fast);
+  run(fast, queue);
   // an optimistic reduction hit its rare case somewhere in this CTA's points: redo the tile exactly
   if (__syncthreads_or(fast.rare))
 #endif
   {
     gl::Exact exact;
-    run(exact);
+    run(exact, queue + 1);
   }
   __syncthreads();
   // ---- phase 3: sum the groups, divide by Z_H (prover.rs:985-991) ----
