@@ -203,6 +203,10 @@ int p2b_mgpu_batch_get_cap(const p2b_mgpu_batch* b, uint64_t* out /* [2^cap_heig
 int p2b_mgpu_batch_open_rows(const p2b_mgpu_batch* b, const uint64_t* leaf_indices, uint64_t count, uint64_t* rows_out,
                              uint64_t* siblings_out /* or NULL */);
 int p2b_mgpu_batch_get_leaves(const p2b_mgpu_batch* b, uint64_t first_leaf, uint64_t count, uint64_t* out);
+/* PolynomialBatch::from_coeffs (fri/oracle.rs:911-977) when every device already holds the coefficient matrix [P][n]
+ * (d_coeffs[index] = device `index`'s copy), e.g. the quotient chunks produced by p2b_mgpu_quotient_polys. */
+int p2b_mgpu_commit_from_device_coeffs(p2b_mgpu* g, const uint64_t* const* d_coeffs, uint32_t degree_log, uint64_t num_polys,
+                                       uint32_t rate_bits, uint32_t cap_height, p2b_mgpu_batch** out);
 
 /* ---------------------------------------------------------------------------------------------------
  * Quotient polynomials: compute_quotient_polys (plonky2/src/plonk/prover.rs:790-1034) for a circuit given as data.
@@ -367,6 +371,24 @@ int p2b_memcpy_d2h(p2b_ctx* ctx, void* h_dst, const void* d_src, uint64_t bytes)
  * timing is taken on the stream the kernels are launched on). */
 int p2b_timer_start(p2b_ctx* ctx);
 int p2b_timer_stop_ms(p2b_ctx* ctx, float* ms_out);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Multi-device quotient polynomials and FRI opening proofs (the stages of prove() after a p2b_mgpu commit)
+ * ------------------------------------------------------------------------------------------------- */
+/* compute_quotient_polys (plonk/prover.rs:790-1034) over sharded batches: every device evaluates the points whose leaf rows
+ * it owns (no row crosses NVLink; needs n_dev <= 2^quotient_degree_bits), the compact value vectors are exchanged, and every
+ * device ends with the coefficients [num_challenges][lde_size] in d_coeffs_out[index] (device memory of that device,
+ * caller-allocated) -- ready for p2b_mgpu_commit_from_device_coeffs as [num_challenges * qdf][n] chunks. */
+int p2b_mgpu_quotient_polys(p2b_mgpu* g, const p2b_circuit* circuit, const p2b_mgpu_batch* wires, const p2b_mgpu_batch* zs_partial_products,
+                            const p2b_mgpu_batch* constants_sigmas, const uint64_t* public_inputs_hash, const uint64_t* betas,
+                            const uint64_t* gammas, const uint64_t* alphas, uint64_t* const* d_coeffs_out);
+/* OpeningSet::new's eval_commitment and PolynomialBatch::prove_openings (plonk/proof.rs:313-319, fri/oracle.rs:1046-1110) over
+ * sharded oracles: coefficient work on the first device (every shard holds a complete coefficient copy), query rows and
+ * Merkle paths from the devices that own the leaves.  The proof object is read with the p2b_fri_proof_* getters. */
+int p2b_mgpu_eval_openings(p2b_mgpu* g, const p2b_mgpu_batch* b, const uint64_t point[2], uint64_t* out);
+int p2b_mgpu_fri_prove_openings(p2b_mgpu* g, const p2b_mgpu_batch* const* oracles, uint32_t num_oracles,
+                                const p2b_fri_batch_info* batches, uint32_t num_batches, p2b_challenger* challenger,
+                                const p2b_fri_params* params, p2b_fri_proof** out);
 
 /* ---------------------------------------------------------------------------------------------------
  * Reference-compatible symbols (cuda/src/lib.rs:52-145).  Same names, argument order, in-place device

@@ -217,6 +217,11 @@ def lib():
         "p2b_mgpu_batch_get_cap": (i, [vp, vp]),
         "p2b_mgpu_batch_open_rows": (i, [vp, vp, u64, vp, vp]),
         "p2b_mgpu_batch_get_leaves": (i, [vp, u64, u64, vp]),
+        "p2b_mgpu_commit_from_device_coeffs": (i, [vp, C.POINTER(vp), u32, u64, u32, u32, C.POINTER(vp)]),
+        "p2b_mgpu_quotient_polys": (i, [vp, C.POINTER(CircuitStruct), vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
+        "p2b_mgpu_eval_openings": (i, [vp, vp, vp, vp]),
+        "p2b_mgpu_fri_prove_openings": (i, [vp, C.POINTER(vp), u32, C.POINTER(FriBatchInfoStruct), u32, C.POINTER(ChallengerStruct),
+                                            C.POINTER(FriParamsStruct), C.POINTER(vp)]),
         "fft_blinding": (RustError, [vp, vp, i, i, i, vp, vp, i, i, vp]),
         # reference-compatible symbols (cuda/src/lib.rs:52-145)
         "init": (None, []),
@@ -558,6 +563,22 @@ def fri_prove_openings(ctx, oracles, batches, challenger, degree_bits, rate_bits
                     [o.degree_log + o.rate_bits - o.cap_height for o in oracles])
 
 
+def _fri_args(batches, degree_bits, rate_bits, cap_height, proof_of_work_bits, num_query_rounds, reduction_arity_bits):
+    keep = []
+    bstructs = (FriBatchInfoStruct * max(len(batches), 1))()
+    for k, (point, polys) in enumerate(batches):
+        arr = (FriPolyInfo * max(len(polys), 1))()
+        for j, (o, p) in enumerate(polys):
+            arr[j].oracle_index, arr[j].polynomial_index = o, p
+        keep.append(arr)
+        bstructs[k].point[0], bstructs[k].point[1] = int(point[0]) % ORDER, int(point[1]) % ORDER
+        bstructs[k].polynomials, bstructs[k].num_polynomials = arr, len(polys)
+    ab = (C.c_uint32 * max(len(reduction_arity_bits), 1))(*reduction_arity_bits)
+    keep.append(ab)
+    params = FriParamsStruct(degree_bits, rate_bits, cap_height, proof_of_work_bits, num_query_rounds, len(reduction_arity_bits), ab)
+    return bstructs, params, keep
+
+
 class MerkleTree:
     """View of a committed batch's tree (reference: MerkleTree {leaves, digests, cap}, merkle_tree.rs:41-66)."""
 
@@ -757,6 +778,57 @@ class MultiGpu:
         ptr, rounds = C.c_void_p(), C.c_uint64()
         _check(lib().p2b_mgpu_resident_cols(self.handle, index, degree_log, num_polys, C.byref(ptr), C.byref(rounds)))
         return ptr.value, rounds.value
+
+    def _ctx(self, index):
+        return lib().p2b_mgpu_ctx(self.handle, index)
+
+    def commit_from_device_coeffs(self, ptrs, degree_log, num_polys, rate_bits, cap_height):
+        """ptrs[d]: device d's pointer to the full coefficient matrix [num_polys][n]."""
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        h = C.c_void_p()
+        _check(lib().p2b_mgpu_commit_from_device_coeffs(self.handle, arr, degree_log, num_polys, rate_bits, cap_height, C.byref(h)))
+        return MultiGpuBatch(self, h)
+
+    def quotient_polys(self, circuit, wires, zs_pp, consts_sigmas, pih, betas, gammas, alphas):
+        """compute_quotient_polys over sharded batches; returns per-device pointers to [num_challenges][lde_size] coefficients
+        (allocated with p2b_malloc on each device; free with free_device_ptrs)."""
+        L = lib()
+        n_words = circuit.num_challenges * circuit.lde_size
+        ptrs = []
+        for d in range(len(self.devices)):
+            p = C.c_void_p()
+            _check(L.p2b_malloc(self._ctx(d), n_words * 8, C.byref(p)))
+            ptrs.append(p.value)
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        a = lambda x: (C.c_uint64 * len(x))(*[int(v) % ORDER for v in x])   # noqa: E731
+        _check(L.p2b_mgpu_quotient_polys(self.handle, C.byref(circuit.struct), wires.handle, zs_pp.handle, consts_sigmas.handle, a(pih), a(betas),
+                                         a(gammas), a(alphas), arr))
+        return ptrs
+
+    def read_device(self, index, ptr, count):
+        out = np.empty(count, dtype=np.uint64)
+        _check(lib().p2b_memcpy_d2h(self._ctx(index), out.ctypes.data, C.c_void_p(ptr), count * 8))
+        return out
+
+    def free_device_ptrs(self, ptrs):
+        self.synchronize()
+        for d, p in enumerate(ptrs):
+            _check(lib().p2b_free(self._ctx(d), C.c_void_p(p)))
+
+    def eval_openings(self, batch, point):
+        out = np.empty((batch.info.num_polys, 2), dtype=np.uint64)
+        pt = (C.c_uint64 * 2)(int(point[0]) % ORDER, int(point[1]) % ORDER)
+        _check(lib().p2b_mgpu_eval_openings(self.handle, batch.handle, pt, out.ctypes.data))
+        return out
+
+    def fri_prove_openings(self, oracles, batches, challenger, degree_bits, rate_bits, cap_height, proof_of_work_bits, num_query_rounds,
+                           reduction_arity_bits):
+        bstructs, params, keep = _fri_args(batches, degree_bits, rate_bits, cap_height, proof_of_work_bits, num_query_rounds, reduction_arity_bits)
+        handles = (C.c_void_p * max(len(oracles), 1))(*[o.handle for o in oracles])
+        out = C.c_void_p()
+        _check(lib().p2b_mgpu_fri_prove_openings(self.handle, handles, len(oracles), bstructs, len(batches), C.byref(challenger.struct),
+                                                 C.byref(params), C.byref(out)))
+        return FriProof(out, reduction_arity_bits, [o.leaf_len for o in oracles], [o.layers for o in oracles])
 
     def commit_resident(self, degree_log, num_polys, rate_bits, cap_height):
         h = C.c_void_p()

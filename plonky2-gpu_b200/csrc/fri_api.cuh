@@ -94,9 +94,13 @@ extern "C" int p2b_eval_openings(p2b_ctx* c, const p2b_batch* b, const uint64_t 
   return rc;
 }
 
-extern "C" int p2b_fri_prove_openings(p2b_ctx* c, const p2b_batch* const* oracles, uint32_t num_oracles,
-                                      const p2b_fri_batch_info* batches, uint32_t num_batches, p2b_challenger* challenger,
-                                      const p2b_fri_params* params, p2b_fri_proof** out) {
+// `opener` (multi-device provers, mgpu.cuh): when set, the oracles may be shards -- only their coefficient copies are read here
+// -- and the FriInitialTreeProof rows + Merkle paths of oracle o come from opener(o, indices, Q, rows_out, siblings_out), which
+// asks the devices that own the leaves.
+typedef std::function<int(u32, const u64*, u64, u64*, u64*)> fri_opener;
+static int fri_prove_impl(p2b_ctx* c, const p2b_batch* const* oracles, uint32_t num_oracles, const p2b_fri_batch_info* batches,
+                          uint32_t num_batches, p2b_challenger* challenger, const p2b_fri_params* params, const fri_opener* opener,
+                          p2b_fri_proof** out) {
   if (!c || !oracles || !batches || !challenger || !params || !out) return fail(P2B_ERR_INVALID, "NULL argument");
   *out = nullptr;
   if (num_oracles == 0 || num_batches == 0) return fail(P2B_ERR_INVALID, "no oracles / no opening batches");
@@ -110,10 +114,12 @@ extern "C" int p2b_fri_prove_openings(p2b_ctx* c, const p2b_batch* const* oracle
     const p2b_batch* o = oracles[i];
     if (!o || !o->coeffs) return fail(P2B_ERR_INVALID, "oracle %u is NULL or holds no coefficients", i);
     if (o->ctx != c) return fail(P2B_ERR_INVALID, "oracle %u belongs to another context", i);
+    if (opener) continue;
     if (o->info.degree_log != k || o->info.rate_bits != rate_bits)
       return fail(P2B_ERR_INVALID, "oracle %u: degree_log %u / rate_bits %u do not match the FRI parameters (%u / %u)", i,
                   o->info.degree_log, o->info.rate_bits, k, rate_bits);
-    if (o->local_leaves != o->info.num_leaves) return fail(P2B_ERR_UNSUPPORTED, "oracle %u is a shard: gather the rows first", i);
+    if (o->local_leaves != o->info.num_leaves)
+      return fail(P2B_ERR_UNSUPPORTED, "oracle %u is a shard: use p2b_mgpu_fri_prove_openings", i);
   }
   u64 total_arity_bits = 0;
   for (u32 r = 0; r < params->num_reductions; r++) {
@@ -315,7 +321,8 @@ extern "C" int p2b_fri_prove_openings(p2b_ctx* c, const p2b_batch* const* oracle
       pr->depth[o] = oracles[o]->shape.sub_log;
       pr->init_rows[o].resize((size_t)Q * pr->leaf_len[o]);
       pr->init_sibs[o].resize((size_t)Q * pr->depth[o] * 4);
-      if (Q) P2B_TRY(open_impl(oracles[o], pr->indices.data(), Q, pr->init_rows[o].data(), pr->init_sibs[o].data()));
+      if (Q && opener) P2B_TRY((*opener)(o, pr->indices.data(), Q, pr->init_rows[o].data(), pr->init_sibs[o].data()));
+      else if (Q) P2B_TRY(open_impl(oracles[o], pr->indices.data(), Q, pr->init_rows[o].data(), pr->init_sibs[o].data()));
     }
     pr->step_depth.resize(R);
     pr->step_evals.resize(R);
@@ -342,6 +349,12 @@ extern "C" int p2b_fri_prove_openings(p2b_ctx* c, const p2b_batch* const* oracle
   }
   *out = pr;
   return P2B_OK;
+}
+
+extern "C" int p2b_fri_prove_openings(p2b_ctx* c, const p2b_batch* const* oracles, uint32_t num_oracles,
+                                      const p2b_fri_batch_info* batches, uint32_t num_batches, p2b_challenger* challenger,
+                                      const p2b_fri_params* params, p2b_fri_proof** out) {
+  return fri_prove_impl(c, oracles, num_oracles, batches, num_batches, challenger, params, nullptr, out);
 }
 
 extern "C" void p2b_fri_proof_destroy(p2b_fri_proof* p) {

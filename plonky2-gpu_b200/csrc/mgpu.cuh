@@ -193,6 +193,44 @@ extern "C" int p2b_mgpu_timer_stop_ms(p2b_mgpu* g, float* ms_max) {
   return P2B_OK;
 }
 
+// every device pushes its `count` top-layer nodes (layer `top`) to all peers, imports everyone's and finishes the layers above
+static int mgpu_exchange_nodes(p2b_mgpu* g, p2b_mgpu_batch* mb, u32 top, u64 count) {
+  const int G = g->n;
+  for (int d = 0; d < G; d++) {
+    CUDA_TRY(cudaSetDevice(g->ctx[d]->device));
+    P2B_TRY(mgpu_events(g, d, 1));
+    if (g->nodes_elems[d] < (u64)G * count * 4) {
+      if (g->nodes_all[d]) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaFree(g->nodes_all[d]));
+      }
+      CUDA_TRY(cudaMalloc(&g->nodes_all[d], (u64)G * count * 4 * sizeof(u64)));
+      g->nodes_elems[d] = (u64)G * count * 4;
+    }
+  }
+  for (int s = 0; s < G; s++) {
+    p2b_ctx* c = g->ctx[s];
+    CUDA_TRY(cudaSetDevice(c->device));
+    u64* mine = g->nodes_all[s] + (u64)s * count * 4;
+    P2B_TRY(p2b_batch_export_nodes(mb->shard[s], top, (u64)s * count, count, mine));
+    CUDA_TRY(cudaEventRecord(g->ev_ifft[s][0], c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(g->xfer[s], g->ev_ifft[s][0], 0));
+    for (int d = 0; d < G; d++)
+      if (d != s)
+        CUDA_TRY(cudaMemcpyPeerAsync(g->nodes_all[d] + (u64)s * count * 4, g->ctx[d]->device, mine, c->device, count * 4 * sizeof(u64), g->xfer[s]));
+    CUDA_TRY(cudaEventRecord(g->ev_nodes[s], g->xfer[s]));
+  }
+  for (int d = 0; d < G; d++) {
+    p2b_ctx* c = g->ctx[d];
+    CUDA_TRY(cudaSetDevice(c->device));
+    for (int s = 0; s < G; s++)
+      if (s != d) CUDA_TRY(cudaStreamWaitEvent(c->stream, g->ev_nodes[s], 0));
+    P2B_TRY(p2b_batch_import_nodes(mb->shard[d], top, 0, (u64)G * count, g->nodes_all[d]));
+    P2B_TRY(p2b_batch_finish_layers(mb->shard[d], top));
+  }
+  return P2B_OK;
+}
+
 extern "C" void p2b_mgpu_batch_destroy(p2b_mgpu_batch* b) {
   if (!b) return;
   for (p2b_batch* s : b->shard)
@@ -313,39 +351,7 @@ static int mgpu_commit(p2b_mgpu* g, int src, const u64* values, u32 k, u64 P, u3
       top = mb->shard[d]->top_layer;
       count = mb->shard[d]->local_leaves >> top;
     }
-    if (G > 1) {
-      for (int d = 0; d < G; d++) {
-        CUDA_TRY(cudaSetDevice(g->ctx[d]->device));
-        if (g->nodes_elems[d] < (u64)G * count * 4) {
-          if (g->nodes_all[d]) {
-            CUDA_TRY(cudaDeviceSynchronize());
-            CUDA_TRY(cudaFree(g->nodes_all[d]));
-          }
-          CUDA_TRY(cudaMalloc(&g->nodes_all[d], (u64)G * count * 4 * sizeof(u64)));
-          g->nodes_elems[d] = (u64)G * count * 4;
-        }
-      }
-      for (int s = 0; s < G; s++) {
-        p2b_ctx* c = g->ctx[s];
-        CUDA_TRY(cudaSetDevice(c->device));
-        u64* mine = g->nodes_all[s] + (u64)s * count * 4;
-        P2B_TRY(p2b_batch_export_nodes(mb->shard[s], top, (u64)s * count, count, mine));
-        CUDA_TRY(cudaEventRecord(g->ev_ifft[s][0], c->stream));
-        CUDA_TRY(cudaStreamWaitEvent(g->xfer[s], g->ev_ifft[s][0], 0));
-        for (int d = 0; d < G; d++)
-          if (d != s)
-            CUDA_TRY(cudaMemcpyPeerAsync(g->nodes_all[d] + (u64)s * count * 4, g->ctx[d]->device, mine, c->device, count * 4 * sizeof(u64), g->xfer[s]));
-        CUDA_TRY(cudaEventRecord(g->ev_nodes[s], g->xfer[s]));
-      }
-      for (int d = 0; d < G; d++) {
-        p2b_ctx* c = g->ctx[d];
-        CUDA_TRY(cudaSetDevice(c->device));
-        for (int s = 0; s < G; s++)
-          if (s != d) CUDA_TRY(cudaStreamWaitEvent(c->stream, g->ev_nodes[s], 0));
-        P2B_TRY(p2b_batch_import_nodes(mb->shard[d], top, 0, (u64)G * count, g->nodes_all[d]));
-        P2B_TRY(p2b_batch_finish_layers(mb->shard[d], top));
-      }
-    }
+    if (G > 1) P2B_TRY(mgpu_exchange_nodes(g, mb, top, count));
     if (coeffs_host_out)
       for (int d = 0; d < G; d++) {
         CUDA_TRY(cudaSetDevice(g->ctx[d]->device));
@@ -471,4 +477,146 @@ extern "C" int p2b_mgpu_batch_get_leaves(const p2b_mgpu_batch* b, uint64_t first
     done += take;
   }
   return P2B_OK;
+}
+
+// ---- commit from coefficients every device already holds (quotient chunks) -----------------------------------------------
+// d_coeffs[d]: device d's copy of the full coefficient matrix [P][n].  Every device extends and hashes its own coset blocks;
+// only the top-layer nodes are exchanged.  (PolynomialBatch::from_coeffs, fri/oracle.rs:911-977)
+extern "C" int p2b_mgpu_commit_from_device_coeffs(p2b_mgpu* g, const uint64_t* const* d_coeffs, uint32_t degree_log, uint64_t num_polys,
+                                                  uint32_t rate_bits, uint32_t cap_height, p2b_mgpu_batch** out) {
+  if (!g || !d_coeffs || !out) return fail(P2B_ERR_INVALID, "NULL argument");
+  *out = nullptr;
+  const int G = g->n;
+  const u64 R = (u64)1 << rate_bits;
+  if ((u64)G > R) return fail(P2B_ERR_INVALID, "%d devices exceed the 2^rate_bits = %llu coset blocks", G, (unsigned long long)R);
+  p2b_mgpu_batch* mb = new (std::nothrow) p2b_mgpu_batch();
+  if (!mb) return fail(P2B_ERR_OOM, "host allocation failed");
+  mb->g = g;
+  mb->shard.assign(G, nullptr);
+  auto body = [&]() -> int {
+    u32 top = 0;
+    u64 count = 0;
+    for (int d = 0; d < G; d++) {
+      if (!d_coeffs[d]) return fail(P2B_ERR_INVALID, "NULL coefficient pointer for device %d", d);
+      P2B_TRY(p2b_commit_blocks(g->ctx[d], d_coeffs[d], degree_log, num_polys, rate_bits, cap_height, nullptr, (u64)d * (R / G), R / G, &mb->shard[d]));
+      top = mb->shard[d]->top_layer;
+      count = mb->shard[d]->local_leaves >> top;
+    }
+    if (G > 1) P2B_TRY(mgpu_exchange_nodes(g, mb, top, count));
+    return P2B_OK;
+  };
+  int rc = body();
+  if (rc != P2B_OK) {
+    p2b_mgpu_batch_destroy(mb);
+    return rc;
+  }
+  mb->info = mb->shard[0]->info;
+  *out = mb;
+  return P2B_OK;
+}
+
+// ---- quotient polynomials over sharded batches ------------------------------------------------------------------------------
+// compute_quotient_polys (plonk/prover.rs:790-1034) on the devices that hold the rows.  Point i of the quotient domain reads
+// leaf row reverse_bits(i << (rate_bits - qdb)) -- held by the device whose index is reverse_bits(i mod G) -- and, for
+// Z(g x), the row of point i + 2^qdb, which has the same residue mod G as long as G divides 2^qdb: every device evaluates
+// exactly the points whose rows it owns, no row crosses NVLink.  The compact value vectors (2 * 8n / G words per device) are
+// pushed to every peer, interleaved into the natural order and inverse-transformed on every device, so that each ends up
+// with the quotient coefficients [num_challenges][lde_size] it needs to commit the quotient chunks
+// (p2b_mgpu_commit_from_device_coeffs).  d_coeffs_out[d]: device d's output buffer (device pointers, caller-allocated).
+extern "C" int p2b_mgpu_quotient_polys(p2b_mgpu* g, const p2b_circuit* circuit, const p2b_mgpu_batch* wires, const p2b_mgpu_batch* zs_pp,
+                                       const p2b_mgpu_batch* consts_sigmas, const uint64_t* public_inputs_hash, const uint64_t* betas,
+                                       const uint64_t* gammas, const uint64_t* alphas, uint64_t* const* d_coeffs_out) {
+  if (!g || !circuit || !wires || !zs_pp || !consts_sigmas || !d_coeffs_out) return fail(P2B_ERR_INVALID, "NULL argument");
+  const int G = g->n;
+  u32 g_log = 0;
+  while ((1 << g_log) < G) g_log++;
+  const u32 qdf = circuit->quotient_degree_factor;
+  u32 qdb = 0;
+  while ((1u << qdb) < qdf) qdb++;
+  if (g_log > qdb) return fail(P2B_ERR_UNSUPPORTED, "%d devices exceed the 2^quotient_degree_bits = %u point classes", G, 1u << qdb);
+  const u32 nc = circuit->num_challenges;
+  const u64 lde_size = (u64)1 << (circuit->degree_bits + qdb), count = lde_size >> g_log;
+  for (const p2b_mgpu_batch* b : {wires, zs_pp, consts_sigmas})
+    if ((int)b->shard.size() != G || b->info.degree_log != circuit->degree_bits || b->info.rate_bits != circuit->rate_bits)
+      return fail(P2B_ERR_INVALID, "batch does not match the device group / circuit shape");
+  std::vector<u64*> parts(G, nullptr), vals(G, nullptr);
+  auto body = [&]() -> int {
+    for (int d = 0; d < G; d++) {
+      p2b_ctx* c = g->ctx[d];
+      CUDA_TRY(cudaSetDevice(c->device));
+      CUDA_TRY(cudaMallocAsync(&parts[d], (u64)G * nc * count * sizeof(u64), c->stream));
+      CUDA_TRY(cudaMallocAsync(&vals[d], (u64)nc * lde_size * sizeof(u64), c->stream));
+      CUDA_TRY(cudaEventRecord(g->ev_done[d], c->stream));
+    }
+    for (int s = 0; s < G; s++)
+      for (int d = 0; d < G; d++) {
+        CUDA_TRY(cudaSetDevice(g->ctx[s]->device));
+        CUDA_TRY(cudaStreamWaitEvent(g->xfer[s], g->ev_done[d], 0));
+      }
+    for (int d = 0; d < G; d++) {
+      p2b_ctx* c = g->ctx[d];
+      CUDA_TRY(cudaSetDevice(c->device));
+      const p2b_batch *w = wires->shard[d], *z = zs_pp->shard[d], *k = consts_sigmas->shard[d];
+      u64 rev = 0;   // points i = reverse_bits(d) (mod G)
+      for (u32 t = 0; t < g_log; t++) rev |= (((u64)d >> t) & 1) << (g_log - 1 - t);
+      u64* mine = parts[d] + (u64)d * nc * count;
+      P2B_TRY(quotient_impl(c, circuit, w->leaves - w->first_leaf * w->info.leaf_len, w->info.leaf_len,
+                            z->leaves - z->first_leaf * z->info.leaf_len, z->info.leaf_len,
+                            k->leaves - k->first_leaf * k->info.leaf_len, k->info.leaf_len, public_inputs_hash, betas, gammas, alphas, mine,
+                            nullptr, nullptr, rev, (u64)G, w->first_leaf + w->local_leaves - 1));
+      P2B_TRY(mgpu_events(g, d, 1));
+      CUDA_TRY(cudaEventRecord(g->ev_ifft[d][0], c->stream));
+      CUDA_TRY(cudaStreamWaitEvent(g->xfer[d], g->ev_ifft[d][0], 0));
+      for (int t = 0; t < G; t++)
+        if (t != d)
+          CUDA_TRY(cudaMemcpyPeerAsync(parts[t] + (u64)d * nc * count, g->ctx[t]->device, mine, c->device, (u64)nc * count * sizeof(u64), g->xfer[d]));
+      CUDA_TRY(cudaEventRecord(g->ev_nodes[d], g->xfer[d]));
+    }
+    for (int d = 0; d < G; d++) {
+      p2b_ctx* c = g->ctx[d];
+      CUDA_TRY(cudaSetDevice(c->device));
+      for (int s = 0; s < G; s++)
+        if (s != d) CUDA_TRY(cudaStreamWaitEvent(c->stream, g->ev_nodes[s], 0));
+      quotient::interleave_parts_kernel<<<(unsigned)((lde_size + 255) / 256), 256, 0, c->stream>>>(parts[d], vals[d], lde_size, nc, g_log);
+      c->launches++;
+      CUDA_TRY(cudaGetLastError());
+      if (!d_coeffs_out[d]) return fail(P2B_ERR_INVALID, "NULL output pointer for device %d", d);
+      P2B_TRY(quotient_values_to_coeffs(c, vals[d], d_coeffs_out[d], circuit->degree_bits + qdb, nc));
+    }
+    return P2B_OK;
+  };
+  int rc = body();
+  for (int d = 0; d < G; d++) {
+    cudaSetDevice(g->ctx[d]->device);
+    // the peers' pushes into parts[d] must have landed before it is returned to the pool: the interleave kernel on this
+    // device's stream waited for them, and the frees below are ordered behind it
+    if (parts[d]) cudaFreeAsync(parts[d], g->ctx[d]->stream);
+    if (vals[d]) cudaFreeAsync(vals[d], g->ctx[d]->stream);
+  }
+  return rc;
+}
+
+// ---- FRI opening proof over sharded oracles -----------------------------------------------------------------------------------
+// PolynomialBatch::prove_openings (fri/oracle.rs:1046-1110).  Everything that reads coefficients (the batch reduction, the
+// commit phase, grinding) runs on the first device, whose shards hold complete coefficient copies; the FriInitialTreeProof
+// rows and Merkle paths of every query come from the devices that own the leaves (p2b_mgpu_batch_open_rows).
+extern "C" int p2b_mgpu_fri_prove_openings(p2b_mgpu* g, const p2b_mgpu_batch* const* oracles, uint32_t num_oracles,
+                                           const p2b_fri_batch_info* batches, uint32_t num_batches, p2b_challenger* challenger,
+                                           const p2b_fri_params* params, p2b_fri_proof** out) {
+  if (!g || !oracles || !out) return fail(P2B_ERR_INVALID, "NULL argument");
+  std::vector<const p2b_batch*> first(num_oracles);
+  for (u32 o = 0; o < num_oracles; o++) {
+    if (!oracles[o] || oracles[o]->shard.empty()) return fail(P2B_ERR_INVALID, "oracle %u is NULL", o);
+    first[o] = oracles[o]->shard[0];
+  }
+  P2B_TRY(p2b_mgpu_synchronize(g));   // the commits that produced the shards (other devices' streams) are complete
+  fri_opener opener = [&](u32 o, const u64* idx, u64 Q, u64* rows, u64* sibs) -> int {
+    return p2b_mgpu_batch_open_rows(oracles[o], idx, Q, rows, sibs);
+  };
+  return fri_prove_impl(g->ctx[0], first.data(), num_oracles, batches, num_batches, challenger, params, &opener, out);
+}
+// OpeningSet::new's eval_commitment (plonk/proof.rs:313-319) for one sharded batch: from the first device's coefficient copy
+extern "C" int p2b_mgpu_eval_openings(p2b_mgpu* g, const p2b_mgpu_batch* b, const uint64_t point[2], uint64_t* out) {
+  if (!g || !b || b->shard.empty()) return fail(P2B_ERR_INVALID, "NULL argument");
+  return p2b_eval_openings(g->ctx[0], b->shard[0], point, out);
 }

@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <algorithm>
 #include <new>
@@ -1287,10 +1288,32 @@ extern "C" int p2b_timer_stop_ms(p2b_ctx* c, float* ms_out) {
 // ======================================================================================================
 // quotient polynomials (plonky2/src/plonk/prover.rs:790-1034)
 // ======================================================================================================
+// coset_ifft(F::coset_shift()) per challenge (prover.rs:1014-1021, polynomial/mod.rs:64-77): values [nc][2^lde_log] -> coefficients
+static int quotient_values_to_coeffs(p2b_ctx* c, const u64* vals, u64* d_coeffs_out, u32 lde_log, u32 nc) {
+  cudaStream_t st = c->stream;
+  const u64 lde_size = (u64)1 << lde_log;
+  Plan pl = make_plan(lde_log);
+  u64* tmp = d_coeffs_out;
+  if (pl.n_strided) {
+    P2B_TRY(ensure_scratch(c, nc * lde_size));
+    tmp = c->scratch;
+  }
+  P2B_TRY(run_ifft(c, vals, d_coeffs_out, tmp, lde_log, nc));
+  quotient::scale_by_powers_kernel<<<(unsigned)((lde_size + 255) / 256), 256, 0, st>>>(d_coeffs_out, lde_size, nc, hostf::inv(hostf::COSET_SHIFT));
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  return P2B_OK;
+}
+
 static int quotient_impl(p2b_ctx* c, const p2b_circuit* circ, const u64* d_wires, u64 wires_stride, const u64* d_zs_pp,
                          u64 zs_stride, const u64* d_cs, u64 cs_stride, const u64* pih, const u64* betas, const u64* gammas,
-                         const u64* alphas, u64* d_values_out, u64* d_coeffs_out, u64* d_rows_out) {
+                         const u64* alphas, u64* d_values_out, u64* d_coeffs_out, u64* d_rows_out, u64 pt_first = 0, u64 pt_stride = 1,
+                         u64 last_row = ~(u64)0) {
+  // pt_first / pt_stride: evaluate only the points i = pt_first + pt_stride * j (a device of a multi-device prover owns the
+  // points whose rows it holds, mgpu.cuh); the row pointers are then "virtual" bases (shard pointer - first_leaf * stride)
+  // and last_row the last leaf row the shard holds.  Values come out compact: [nc][lde_size / pt_stride].
   if (!c || !circ || !d_wires || !d_zs_pp || !d_cs || !pih || !betas || !gammas || !alphas) return fail(P2B_ERR_INVALID, "NULL argument");
+  if (pt_stride != 1 && d_coeffs_out) return fail(P2B_ERR_INVALID, "coefficients need the values of the whole domain");
   Stage stage(c, c->stream, "compute quotient polys");   // plonk/prover.rs:187-196
   if (!circ->gates && circ->num_gates) return fail(P2B_ERR_INVALID, "NULL gate list");
   if (!circ->k_is && circ->num_routed_wires) return fail(P2B_ERR_INVALID, "NULL k_is");
@@ -1388,6 +1411,10 @@ static int quotient_impl(p2b_ctx* c, const p2b_circuit* circ, const u64* d_wires
       CUDA_TRY(cudaMallocAsync(&d_vals, nc * lde_size * sizeof(u64), st));
       vals = d_vals;
     }
+    p.pt_first = pt_first;
+    p.pt_stride = pt_stride;
+    p.pt_count = lde_size / pt_stride;
+    p.last_row = last_row == ~(u64)0 ? (((u64)1 << (circ->degree_bits + circ->rate_bits)) - 1) : last_row;
     p.gates = d_gates;
     p.k_is = d_kis;
     p.alpha_pows = d_apows;
@@ -1422,45 +1449,31 @@ static int quotient_impl(p2b_ctx* c, const p2b_circuit* circ, const u64* d_wires
       CUDA_TRY(cudaMemcpyAsync(d_work, flat.data(), flat.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
       CUDA_TRY(cudaStreamSynchronize(st));   // flat goes out of scope
       const u32 num_items = (u32)flat.size();
-      const u64 matrix_rows = (u64)1 << (circ->degree_bits + circ->rate_bits);
-      const unsigned blocks = (unsigned)((lde_size + tg.points() - 1) / tg.points());
+      const unsigned blocks = (unsigned)((p.pt_count + tg.points() - 1) / tg.points());
       const size_t smem = tg.words() * sizeof(u64);
       constexpr unsigned BD = quotient::QUOT_WARPS * 32;
       switch (nc) {
         case 1:
           P2B_TRY(opt_in_smem(quotient::quotient_values_kernel<1>, smem));
-          quotient::quotient_values_kernel<1><<<blocks, BD, smem, st>>>(p, tg, d_work, num_items, matrix_rows);
+          quotient::quotient_values_kernel<1><<<blocks, BD, smem, st>>>(p, tg, d_work, num_items);
           break;
         case 2:
           P2B_TRY(opt_in_smem(quotient::quotient_values_kernel<2>, smem));
-          quotient::quotient_values_kernel<2><<<blocks, BD, smem, st>>>(p, tg, d_work, num_items, matrix_rows);
+          quotient::quotient_values_kernel<2><<<blocks, BD, smem, st>>>(p, tg, d_work, num_items);
           break;
         case 3:
           P2B_TRY(opt_in_smem(quotient::quotient_values_kernel<3>, smem));
-          quotient::quotient_values_kernel<3><<<blocks, BD, smem, st>>>(p, tg, d_work, num_items, matrix_rows);
+          quotient::quotient_values_kernel<3><<<blocks, BD, smem, st>>>(p, tg, d_work, num_items);
           break;
         default:
           P2B_TRY(opt_in_smem(quotient::quotient_values_kernel<4>, smem));
-          quotient::quotient_values_kernel<4><<<blocks, BD, smem, st>>>(p, tg, d_work, num_items, matrix_rows);
+          quotient::quotient_values_kernel<4><<<blocks, BD, smem, st>>>(p, tg, d_work, num_items);
           break;
       }
     }
     c->launches++;
     CUDA_TRY(cudaGetLastError());
-    if (d_coeffs_out) {
-      // coset_ifft(F::coset_shift()) per challenge (prover.rs:1014-1021, polynomial/mod.rs:64-77)
-      Plan pl = make_plan(lde_log);
-      u64* tmp = d_coeffs_out;
-      if (pl.n_strided) {
-        P2B_TRY(ensure_scratch(c, nc * lde_size));
-        tmp = c->scratch;
-      }
-      P2B_TRY(run_ifft(c, vals, d_coeffs_out, tmp, lde_log, nc));
-      quotient::scale_by_powers_kernel<<<(unsigned)((lde_size + 255) / 256), 256, 0, st>>>(d_coeffs_out, lde_size, nc,
-                                                                                     hostf::inv(hostf::COSET_SHIFT));
-      c->launches++;
-      CUDA_TRY(cudaGetLastError());
-    }
+    if (d_coeffs_out) P2B_TRY(quotient_values_to_coeffs(c, vals, d_coeffs_out, lde_log, nc));
     return P2B_OK;
   };
   int rc = body();

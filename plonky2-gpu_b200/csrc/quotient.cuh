@@ -55,8 +55,12 @@ struct Params {
   u64 w;                                // generator of the evaluation subgroup (order 2^(degree_bits + qdb))
   u64 n_field;                          // n as a field element
   u64 small_roots[9];                   // primitive_root_of_unity(k), k <= 8 (interpolation gates' cosets)
-  u64* out_values;                      // [num_challenges][lde_size]
-  u64* out_rows;                        // optional [lde_size][num_challenges] (the reference's d_outs layout)
+  u64* out_values;                      // [num_challenges][pt_count]
+  u64* out_rows;                        // optional [pt_count][num_challenges] (the reference's d_outs layout)
+  // the points this launch evaluates: i = pt_first + pt_stride * j, j < pt_count (the whole domain: 0, 1, lde_size).  A device
+  // of a multi-device prover owns the points whose rows lie in its leaf range: i = rev(d) mod G (csrc/mgpu.cuh).
+  u64 pt_first, pt_stride, pt_count;
+  u64 last_row;                         // index of the last leaf row the three matrices hold (copied without over-read)
 };
 
 // host: number of constraints of a gate (each gate's num_constraints())
@@ -617,7 +621,7 @@ __device__ __forceinline__ void stage_row(u64* slot, const u64* src, u32 nwords,
 
 template <int NC>
 __global__ void __launch_bounds__(QUOT_WARPS * 32) quotient_values_kernel(Params p, TileGeom tg, const u32* __restrict__ work_items,
-                                                                          u32 num_items, u64 matrix_rows) {
+                                                                          u32 num_items) {
   extern __shared__ __align__(16) u64 qsh[];
   const u32 TP = tg.points(), G = tg.groups();
   // layout: [mbar (2 words)] [queue: counters (2 x u32), per-group item slots (2 x 12 x u32)] [wires TP x ws] [cs TP x css]
@@ -633,7 +637,7 @@ __global__ void __launch_bounds__(QUOT_WARPS * 32) quotient_values_kernel(Params
   __shared__ const u64* row_cs[QUOT_WARPS * 32 / 2];
   __shared__ const u64* row_zs[QUOT_WARPS * 32 / 2];
   const u64 lde_size = (u64)1 << (p.degree_bits + p.qdb);
-  const u64 tile_first = (u64)blockIdx.x * TP;
+  const u64 tile_first = (u64)blockIdx.x * TP;   // in units of this launch's point list (j)
   const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const u32 lde_bits = p.degree_bits + p.rate_bits, step_log = p.rate_bits - p.qdb;
 
@@ -646,14 +650,15 @@ __global__ void __launch_bounds__(QUOT_WARPS * 32) quotient_values_kernel(Params
   }
   __syncthreads();
   if (tid < TP) {
-    u64 i = tile_first + tid;
-    if (i >= lde_size) i = lde_size - 1;  // tail slots recompute the last point; their results are not stored
+    u64 j = tile_first + tid;
+    if (j >= p.pt_count) j = p.pt_count - 1;  // tail slots recompute the last point; their results are not stored
+    const u64 i = p.pt_first + p.pt_stride * j;
     const u64 row = lde_bits ? (__brevll(i << step_log) >> (64 - lde_bits)) : 0;
     const u64 i_next = (i + ((u64)1 << p.qdb)) & (lde_size - 1);
     const u64 row_next = lde_bits ? (__brevll(i_next << step_log) >> (64 - lde_bits)) : 0;
     u64 *rw, *rc, *rz;
     // the last row of a matrix may not be followed by a readable word: it is copied with ordinary loads
-    const bool last = row + 1 == matrix_rows;
+    const bool last = row == p.last_row;
     if (!last) {
       stage_row(sw + (size_t)tid * tg.ws, p.wires + row * p.wires_stride, tg.nw, mbar, &rw);
       stage_row(scs + (size_t)tid * tg.css, p.cs + row * p.cs_stride, tg.ncs, mbar, &rc);
@@ -685,7 +690,7 @@ __global__ void __launch_bounds__(QUOT_WARPS * 32) quotient_values_kernel(Params
 
   // ---- phase 2: warp (group, point warp) evaluates its group's work items for its 32 points ----
   const u32 group = wid / tg.tw, slot = (wid % tg.tw) * 32 + lane;
-  const u64 i = min(tile_first + slot, lde_size - 1);
+  const u64 i = p.pt_first + p.pt_stride * min(tile_first + slot, p.pt_count - 1);
   PointRows r;
   r.w = row_w[slot];
   r.cs = row_cs[slot];
@@ -731,16 +736,16 @@ __global__ void __launch_bounds__(QUOT_WARPS * 32) quotient_values_kernel(Params
   }
   __syncthreads();
   // ---- phase 3: sum the groups, divide by Z_H (prover.rs:985-991) ----
-  if (tid < TP && tile_first + tid < lde_size) {
-    const u64 pi = tile_first + tid;
+  if (tid < TP && tile_first + tid < p.pt_count) {
+    const u64 pj = tile_first + tid, pi = p.pt_first + p.pt_stride * pj;
     const u64 zi = p.zh_inv[pi & ((1u << p.qdb) - 1)];
 #pragma unroll
     for (int c = 0; c < NC; c++) {
       u64 v = 0;
       for (u32 g2 = 0; g2 < G; g2++) v = gl::add(v, part[((size_t)g2 * NC + c) * TP + tid]);
       v = gl::canon(gl::mul(v, zi));
-      p.out_values[(u64)c * lde_size + pi] = v;
-      if (p.out_rows) p.out_rows[pi * NC + c] = v;
+      p.out_values[(u64)c * p.pt_count + pj] = v;
+      if (p.out_rows) p.out_rows[pj * NC + c] = v;
     }
   }
 }
@@ -772,6 +777,17 @@ inline u64 work_item_cost(const Params& p, const GateDesc* g) {
     default: break;
   }
   return k * emit + extra + 200;
+}
+
+// multi-device: values[c][i] <- parts[(src(i) * nc + c) * count + i / G] where device src(i) = reverse_bits(i mod G) evaluated
+// the points congruent to i mod G (csrc/mgpu.cuh)
+__global__ void interleave_parts_kernel(const u64* __restrict__ parts, u64* __restrict__ values, u64 lde_size, u32 nc, u32 g_log) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= lde_size) return;
+  const u64 G = (u64)1 << g_log, count = lde_size >> g_log;
+  const u64 res = i & (G - 1);
+  const u64 src = g_log ? (__brevll(res) >> (64 - g_log)) : 0;
+  for (u32 c = 0; c < nc; c++) values[(u64)c * lde_size + i] = parts[(src * nc + c) * count + (i >> g_log)];
 }
 
 // coefficients[i] *= shift_inv^i  (coset_ifft, field/src/polynomial/mod.rs:64-77)

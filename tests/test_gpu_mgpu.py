@@ -73,3 +73,72 @@ def test_c_program_drives_the_devices_from_one_process(tmp_path):
     r = subprocess.run([exe, str(ndev), "12", "135"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.startswith("OK")
+
+
+def _gpu_counts():
+    return [g for g in (1, 2, 4, 8)]
+
+
+@pytest.mark.parametrize("ndev", _gpu_counts())
+def test_mgpu_prove_stages_match_single_device(ndev):
+    """Quotient polynomials, quotient-chunk commit, openings and the FRI opening proof over SHARDED batches (one process, ndev
+    devices) equal the single-device results bit for bit: plonk/prover.rs:884-1034, fri/oracle.rs:1046-1110."""
+    if _ngpu() < ndev:
+        pytest.skip("needs %d GPUs" % ndev)
+    from tests import quotient_fixtures as F
+    p2b.build()
+    gates, groups, sel = F.recursion_gate_set()
+    inst = F.build_instance(gates, groups, sel, 6, 135, 80, seed=33)
+    circ = inst.circ
+    ctx = p2b.Context(0)
+    mg = p2b.MultiGpu(count=ndev)
+    rb, ch = circ.rate_bits, 2
+    mats = [inst.consts_sigmas, inst.wires, inst.zs_pp]
+    single = [p2b.PolynomialBatch.from_values(ctx, m, rb, ch) for m in mats]
+    multi = [mg.commit_from_values(np.ascontiguousarray(m, dtype=np.uint64), rb, ch) for m in mats]
+    for a, b in zip(single, multi):
+        assert np.array_equal(a.cap(), b.cap())
+    pc = p2b.Circuit([(g.type_id, g.params) for g in circ.gates], circ.selector_indices, circ.groups, circ.num_wires, circ.num_routed_wires,
+                     circ.num_constants, circ.k_is, circ.degree_bits, circ.rate_bits, circ.num_challenges, circ.quotient_degree_factor)
+    import ctypes as C
+    size, nc = pc.lde_size, pc.num_challenges
+    dv, dc = p2b.DeviceBuffer(ctx, nc * size), p2b.DeviceBuffer(ctx, nc * size)
+    arr = lambda x: (C.c_uint64 * len(x))(*[int(v) for v in x])   # noqa: E731
+    p2b._check(p2b.lib().p2b_quotient_polys(ctx.handle, C.byref(pc.struct), single[1].handle, single[2].handle, single[0].handle, arr(inst.pih),
+                                            arr(inst.betas), arr(inst.gammas), arr(inst.alphas), dv.ptr, dc.ptr))
+    want_coeffs = dc.to_host(nc * size)
+    ptrs = mg.quotient_polys(pc, multi[1], multi[2], multi[0], inst.pih, inst.betas, inst.gammas, inst.alphas)
+    for d in range(ndev):
+        assert np.array_equal(mg.read_device(d, ptrs[d], nc * size), want_coeffs), d
+    # quotient chunks: [nc][8 n] coefficients are [nc * 8][n] chunk-major (prover.rs:151-166)
+    n_log = circ.degree_bits
+    qdf = 8
+    bq_s = p2b.PolynomialBatch.from_coeffs(ctx, (dc, nc * qdf, 1 << n_log), rb, ch)
+    bq_m = mg.commit_from_device_coeffs(ptrs, n_log, nc * qdf, rb, ch)
+    assert np.array_equal(bq_s.cap(), bq_m.cap())
+    # openings + FRI proof over the four oracles
+    zeta = (0x1234567, 0x7654321)
+    for a, b in zip(single + [bq_s], multi + [bq_m]):
+        assert np.array_equal(p2b.eval_openings(ctx, a, zeta), mg.eval_openings(b, zeta))
+    polys = [m.shape[0] for m in mats] + [nc * qdf]
+    all_polys = [(o, p) for o, k in enumerate(polys) for p in range(k)]
+    batches = [(zeta, all_polys), ((5, 9), [(2, 0), (2, 1)])]
+    args = (n_log, rb, ch, 6, 5, [2, 1])
+    c1, c2 = p2b.Challenger(list(range(12)), [3, 4]), p2b.Challenger(list(range(12)), [3, 4])
+    ps = p2b.fri_prove_openings(ctx, single + [bq_s], batches, c1, *args)
+    pm = mg.fri_prove_openings(multi + [bq_m], batches, c2, *args)
+    assert ps.pow_witness == pm.pow_witness and ps.query_indices == pm.query_indices
+    assert np.array_equal(ps.final_poly, pm.final_poly)
+    assert all(np.array_equal(a, b) for a, b in zip(ps.commit_phase_merkle_caps, pm.commit_phase_merkle_caps))
+    for (r1, s1), (r2, s2) in zip(ps.initial, pm.initial):
+        assert np.array_equal(r1, r2) and np.array_equal(s1, s2)
+    for (e1, s1), (e2, s2) in zip(ps.steps, pm.steps):
+        assert np.array_equal(e1, e2) and np.array_equal(s1, s2)
+    assert list(c1.struct.sponge_state) == list(c2.struct.sponge_state)
+    ps.close()
+    pm.close()
+    mg.free_device_ptrs(ptrs)
+    for b in single + [bq_s] + multi + [bq_m]:
+        b.close()
+    mg.close()
+    ctx.close()
