@@ -189,6 +189,10 @@ int p2b_mgpu_timer_stop_ms(p2b_mgpu* g, float* ms_max); /* ... longest span over
  * the transforms; it must stay valid until p2b_mgpu_synchronize); coeffs_host_out NULL or [P][n] (valid after the same). */
 int p2b_mgpu_commit_from_values(p2b_mgpu* g, const uint64_t* values_host, uint32_t degree_log, uint64_t num_polys,
                                 uint32_t rate_bits, uint32_t cap_height, uint64_t* coeffs_host_out, p2b_mgpu_batch** out);
+/* The value matrix [P][n] sits on ONE device of the group (index src_index; e.g. Z / partial products computed there): its
+ * columns are pushed to their owners over NVLink, then the commit proceeds as above. */
+int p2b_mgpu_commit_from_device_values(p2b_mgpu* g, int src_index, const uint64_t* d_values, uint32_t degree_log, uint64_t num_polys,
+                                       uint32_t rate_bits, uint32_t cap_height, p2b_mgpu_batch** out);
 /* Inputs already resident on the devices.  The columns are dealt in exchange rounds of 8, 8, 16, 32, .. 8*n_dev consecutive
  * columns (p2b_mgpu_round); device `index` holds, for round j, its `per` columns [col0 + index*per, ...) at rows
  * [row0, row0 + per) of its local buffer [sum of per][n] (zero rows where a round is ragged).  The commit transforms them in place. */

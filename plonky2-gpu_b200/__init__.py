@@ -218,6 +218,7 @@ def lib():
         "p2b_mgpu_batch_open_rows": (i, [vp, vp, u64, vp, vp]),
         "p2b_mgpu_batch_get_leaves": (i, [vp, u64, u64, vp]),
         "p2b_mgpu_commit_from_device_coeffs": (i, [vp, C.POINTER(vp), u32, u64, u32, u32, C.POINTER(vp)]),
+        "p2b_mgpu_commit_from_device_values": (i, [vp, i, vp, u32, u64, u32, u32, C.POINTER(vp)]),
         "p2b_mgpu_quotient_polys": (i, [vp, C.POINTER(CircuitStruct), vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]),
         "p2b_mgpu_eval_openings": (i, [vp, vp, vp, vp]),
         "p2b_mgpu_fri_prove_openings": (i, [vp, C.POINTER(vp), u32, C.POINTER(FriBatchInfoStruct), u32, C.POINTER(ChallengerStruct),
@@ -304,15 +305,19 @@ class PinnedBuffer:
 class Context:
     """Per-device context (replaces the reference's CudaInvContext, fri/oracle.rs:75-109)."""
 
-    def __init__(self, device=-1):
+    def __init__(self, device=-1, _borrowed=None):
+        self._owned = _borrowed is None
+        if _borrowed is not None:          # a context owned by a MultiGpu group (MultiGpu.context)
+            self.handle = _borrowed
+            return
         h = C.c_void_p()
         _check(lib().p2b_ctx_create(device, C.byref(h)))
         self.handle = h.value
 
     def close(self):
-        if self.handle:
+        if self.handle and self._owned:
             lib().p2b_ctx_destroy(self.handle)
-            self.handle = None
+        self.handle = None
 
     def __del__(self):
         try:
@@ -781,6 +786,16 @@ class MultiGpu:
 
     def _ctx(self, index):
         return lib().p2b_mgpu_ctx(self.handle, index)
+
+    def context(self, index):
+        """Device `index`'s context as a Context object (owned by the group: closing it is a no-op)."""
+        return Context(_borrowed=self._ctx(index))
+
+    def commit_from_device_values(self, src_index, ptr, degree_log, num_polys, rate_bits, cap_height):
+        """ptr: device pointer on device `src_index` to the value matrix [num_polys][n]."""
+        h = C.c_void_p()
+        _check(lib().p2b_mgpu_commit_from_device_values(self.handle, src_index, C.c_void_p(ptr), degree_log, num_polys, rate_bits, cap_height, C.byref(h)))
+        return MultiGpuBatch(self, h)
 
     def commit_from_device_coeffs(self, ptrs, degree_log, num_polys, rate_bits, cap_height):
         """ptrs[d]: device d's pointer to the full coefficient matrix [num_polys][n]."""

@@ -24,6 +24,7 @@ struct p2b_mgpu {
   std::vector<std::vector<cudaEvent_t>> ev_ifft;  // [device][round]
   std::vector<std::vector<cudaEvent_t>> ev_push;  // [device][round]
   std::vector<cudaEvent_t> ev_nodes, ev_t0, ev_t1, ev_done;
+  std::vector<std::vector<cudaEvent_t>> ev_fwd;   // [device]: events of that device's copy stream (ONE_DEVICE source forwarding)
   std::vector<u64*> cols;                         // per device: its column blocks [rounds * 8][n]
   std::vector<u64> cols_elems;
   std::vector<u64*> nodes_all;                    // per device: gathered top-layer nodes
@@ -79,6 +80,7 @@ extern "C" void p2b_mgpu_destroy(p2b_mgpu* g) {
     cudaStreamSynchronize(g->ctx[d]->stream);
     for (cudaEvent_t e : g->ev_ifft[d]) cudaEventDestroy(e);
     for (cudaEvent_t e : g->ev_push[d]) cudaEventDestroy(e);
+    for (cudaEvent_t e : g->ev_fwd[d]) cudaEventDestroy(e);
     for (cudaEvent_t e : {g->ev_nodes[d], g->ev_t0[d], g->ev_t1[d], g->ev_done[d]})
       if (e) cudaEventDestroy(e);
     if (g->cols[d]) cudaFree(g->cols[d]);
@@ -99,6 +101,7 @@ extern "C" int p2b_mgpu_create(const int* devices, int n_dev, p2b_mgpu** out) {
   g->xfer.assign(n_dev, nullptr);
   g->ev_ifft.resize(n_dev);
   g->ev_push.resize(n_dev);
+  g->ev_fwd.resize(n_dev);
   g->ev_nodes.assign(n_dev, nullptr);
   g->ev_t0.assign(n_dev, nullptr);
   g->ev_t1.assign(n_dev, nullptr);
@@ -242,22 +245,25 @@ extern "C" void p2b_mgpu_batch_destroy(p2b_mgpu_batch* b) {
 }
 
 // where the caller's value columns live
-enum { P2B_MGPU_SRC_HOST = 0, P2B_MGPU_SRC_RESIDENT = 1 };
+enum { P2B_MGPU_SRC_HOST = 0, P2B_MGPU_SRC_RESIDENT = 1, P2B_MGPU_SRC_ONE_DEVICE = 2 };
 
 // PolynomialBatch::from_values over all devices of `g` (fri/oracle.rs:709-731 / :279-545).
 //   src == HOST    : values = host [P][n] (pinned for overlap); uploaded block by block behind the transforms
 //   src == RESIDENT: the column blocks are already on their devices in the layout of p2b_mgpu_resident_cols()
 //                    (what a prover that generates its witness on the GPUs, or a benchmark with inputs in HBM, has)
 //   coeffs_host_out: NULL or host [P][n]; receives the coefficients (the reference keeps them host-side, oracle.rs:403-407)
+//   src == ONE_DEVICE: values = device pointer [P][n] on device index `src_index` (e.g. the Z / partial-product matrix the
+//                    first device just computed): its columns are pushed to their owners over NVLink first
 static int mgpu_commit(p2b_mgpu* g, int src, const u64* values, u32 k, u64 P, u32 rate_bits, u32 cap_height, u64* coeffs_host_out,
-                       p2b_mgpu_batch** out) {
+                       p2b_mgpu_batch** out, int src_index = 0) {
   if (!g || !out) return fail(P2B_ERR_INVALID, "NULL argument");
   *out = nullptr;
   const int G = g->n;
   const u64 R = (u64)1 << rate_bits;
   if ((u64)G > R) return fail(P2B_ERR_INVALID, "%d devices exceed the 2^rate_bits = %llu coset blocks", G, (unsigned long long)R);
   if (P <= 4) return fail(P2B_ERR_UNSUPPORTED, "multi-device commit needs more than 4 polynomials (hash_or_noop copies shorter leaves)");
-  if (src == P2B_MGPU_SRC_HOST && !values) return fail(P2B_ERR_INVALID, "NULL values");
+  if (src != P2B_MGPU_SRC_RESIDENT && !values) return fail(P2B_ERR_INVALID, "NULL values");
+  if (src == P2B_MGPU_SRC_ONE_DEVICE && (src_index < 0 || src_index >= G)) return fail(P2B_ERR_INVALID, "source device index out of range");
   const u64 n = (u64)1 << k;
   u64 rows_total = 0;
   const std::vector<MgpuRound> sched = mgpu_schedule(P, G, &rows_total);
@@ -283,8 +289,10 @@ static int mgpu_commit(p2b_mgpu* g, int src, const u64* values, u32 k, u64 P, u3
       }
       P2B_TRY(ensure_scratch(c, (u64)G * 8 * n));
       P2B_TRY(p2b_commit_blocks_begin(c, k, P, rate_bits, cap_height, (u64)d * (R / G), R / G, &mb->shard[d]));
-      // the peers push into this shard's coefficient matrix: its allocation must precede their copies
+      // the peers push into this shard's coefficient matrix: its allocation must precede their copies; and this device's
+      // column buffer may still be read by an earlier commit: uploads into it are ordered behind the main stream as well
       CUDA_TRY(cudaEventRecord(g->ev_done[d], c->stream));
+      CUDA_TRY(cudaStreamWaitEvent(c->stream_h2d, g->ev_done[d], 0));
     }
     for (int s = 0; s < G; s++)
       for (int d = 0; d < G; d++) {
@@ -320,6 +328,26 @@ static int mgpu_commit(p2b_mgpu* g, int src, const u64* values, u32 k, u64 P, u3
           cudaEvent_t up = c->ev_copy[j % 14];
           CUDA_TRY(cudaMemcpyAsync(blk, values + c0 * n, nc * n * sizeof(u64), cudaMemcpyHostToDevice, c->stream_h2d));
           CUDA_TRY(cudaEventRecord(up, c->stream_h2d));
+          CUDA_TRY(cudaStreamWaitEvent(c->stream, up, 0));
+        } else if (src == P2B_MGPU_SRC_ONE_DEVICE) {
+          // the source device's main stream produced `values`; its copy stream forwards this slice to its owner
+          p2b_ctx* sc = g->ctx[src_index];
+          if (j == 0 && s == 0) {
+            CUDA_TRY(cudaSetDevice(sc->device));
+            CUDA_TRY(cudaEventRecord(sc->ev_a, sc->stream));
+            CUDA_TRY(cudaStreamWaitEvent(g->xfer[src_index], sc->ev_a, 0));
+          }
+          CUDA_TRY(cudaSetDevice(sc->device));
+          CUDA_TRY(cudaMemcpyPeerAsync(blk, c->device, values + c0 * n, sc->device, nc * n * sizeof(u64), g->xfer[src_index]));
+          const size_t slot = (size_t)j * G + s;   // an event of the SOURCE device (events are recorded on their own device's streams)
+          while (g->ev_fwd[src_index].size() <= slot) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            g->ev_fwd[src_index].push_back(e);
+          }
+          cudaEvent_t up = g->ev_fwd[src_index][slot];
+          CUDA_TRY(cudaEventRecord(up, g->xfer[src_index]));
+          CUDA_TRY(cudaSetDevice(c->device));
           CUDA_TRY(cudaStreamWaitEvent(c->stream, up, 0));
         }
         P2B_TRY(run_ifft(c, blk, blk, c->scratch, k, nc));
@@ -378,6 +406,11 @@ static int mgpu_commit(p2b_mgpu* g, int src, const u64* values, u32 k, u64 P, u3
 extern "C" int p2b_mgpu_commit_from_values(p2b_mgpu* g, const uint64_t* values_host, uint32_t degree_log, uint64_t num_polys,
                                            uint32_t rate_bits, uint32_t cap_height, uint64_t* coeffs_host_out, p2b_mgpu_batch** out) {
   return mgpu_commit(g, P2B_MGPU_SRC_HOST, values_host, degree_log, num_polys, rate_bits, cap_height, coeffs_host_out, out);
+}
+
+extern "C" int p2b_mgpu_commit_from_device_values(p2b_mgpu* g, int src_index, const uint64_t* d_values, uint32_t degree_log,
+                                                  uint64_t num_polys, uint32_t rate_bits, uint32_t cap_height, p2b_mgpu_batch** out) {
+  return mgpu_commit(g, P2B_MGPU_SRC_ONE_DEVICE, d_values, degree_log, num_polys, rate_bits, cap_height, nullptr, out, src_index);
 }
 
 // Device-resident input: returns (allocating on first use) device `index`'s local buffer [rows_total][n] in the layout of
