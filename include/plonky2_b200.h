@@ -271,8 +271,9 @@ int p2b_quotient_polys_rows(p2b_ctx* ctx, const p2b_circuit* circuit, const uint
  *   k_is, betas, gammas: host arrays ([num_routed_wires], [num_challenges], [num_challenges])
  *   d_out           column-major [num_challenges * ceil(num_routed_wires / quotient_degree_factor)][n]:
  *                   Z_c for every challenge, then the partial products of challenge 0, 1, ... (canonical values)
- * A zero denominator (probability ~ n * num_routed / p for honest challenges) yields zeros where the reference's
- * batch_multiplicative_inverse would panic.
+ * A zero denominator (probability ~ n * num_routed / p for honest challenges) returns P2B_ERR_INVALID "Tried to invert zero",
+ * where the reference's batch_multiplicative_inverse panics with the same words (field/src/types.rs:130).  The call
+ * synchronises the context's stream before returning (the flag is read back; host arrays may be reused at once).
  * ------------------------------------------------------------------------------------------------- */
 int p2b_partial_products_and_zs(p2b_ctx* ctx, const uint64_t* d_wires_values, const uint64_t* d_sigma_values,
                                 uint32_t degree_bits, uint32_t num_routed_wires, uint32_t quotient_degree_factor,

@@ -359,7 +359,7 @@ extern "C" int p2b_fri_prove_openings(p2b_ctx* c, const p2b_batch* const* oracle
 
 extern "C" void p2b_fri_proof_destroy(p2b_fri_proof* p) {
   if (!p) return;
-  if (p->d_final_in) cudaFreeAsync(p->d_final_in, p->ctx->stream);
+  if (p->d_final_in && ctx_alive(p->ctx)) cudaFreeAsync(p->d_final_in, p->ctx->stream);
   delete p;
 }
 extern "C" int p2b_fri_proof_get_info(const p2b_fri_proof* p, p2b_fri_proof_info* out) {

@@ -237,10 +237,7 @@ static int mgpu_exchange_nodes(p2b_mgpu* g, p2b_mgpu_batch* mb, u32 top, u64 cou
 extern "C" void p2b_mgpu_batch_destroy(p2b_mgpu_batch* b) {
   if (!b) return;
   for (p2b_batch* s : b->shard)
-    if (s) {
-      cudaSetDevice(s->ctx->device);
-      batch_free(s);
-    }
+    if (s) batch_free(s);   // checks that the shard's context is still alive
   delete b;
 }
 

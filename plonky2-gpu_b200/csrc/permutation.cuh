@@ -46,7 +46,8 @@ __device__ __forceinline__ u64 inverse(u64 x) {
 template <int MAXK>
 __global__ void __launch_bounds__(128) chunk_products_kernel(const u64* __restrict__ wires, const u64* __restrict__ sigmas,
                                                              u64 n, u32 n_log, u32 num_routed, u32 degree, u32 nc, Challenges ch,
-                                                             const u64* __restrict__ k_is, u64 w, u64* __restrict__ out) {
+                                                             const u64* __restrict__ k_is, u64 w, u64* __restrict__ out,
+                                                             u32* __restrict__ zero_denominator) {
   const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const u32 K = (num_routed + degree - 1) / degree;
@@ -76,6 +77,9 @@ __global__ void __launch_bounds__(128) chunk_products_kernel(const u64* __restri
       pd[k] = run;  // product of D_0..D_{k-1}
       run = gl::mul(run, D[k]);
     }
+    // the reference's batch_multiplicative_inverse panics on a zero denominator ("Tried to invert zero", types.rs:130): flagged
+    // here, turned into an error by the host entry point
+    if (gl::canon(run) == 0) atomicOr(zero_denominator, 1u);
     u64 inv = inverse(run);
 #pragma unroll
     for (int k = MAXK - 1; k >= 0; k--) {

@@ -153,6 +153,23 @@ struct Stage {
   }
 };
 
+// Live contexts: objects that outlive their context (a binding's finalizers run in any order at process exit) must not touch
+// its streams -- their destructors check here and only drop the host-side record then.
+static std::mutex g_live_mu;
+static std::vector<p2b_ctx*> g_live_ctx;
+static void ctx_register(p2b_ctx* c) {
+  std::lock_guard<std::mutex> lk(g_live_mu);
+  g_live_ctx.push_back(c);
+}
+static void ctx_unregister(p2b_ctx* c) {
+  std::lock_guard<std::mutex> lk(g_live_mu);
+  g_live_ctx.erase(std::remove(g_live_ctx.begin(), g_live_ctx.end(), c), g_live_ctx.end());
+}
+static bool ctx_alive(const p2b_ctx* c) {
+  std::lock_guard<std::mutex> lk(g_live_mu);
+  return std::find(g_live_ctx.begin(), g_live_ctx.end(), c) != g_live_ctx.end();
+}
+
 static int ensure_scratch(p2b_ctx* c, u64 elems) {
   if (c->scratch_elems >= elems) return P2B_OK;
   if (c->scratch) {
@@ -252,12 +269,14 @@ extern "C" int p2b_ctx_create(int device, p2b_ctx** out) {
     delete c;
     return rc;
   }
+  ctx_register(c);
   *out = c;
   return P2B_OK;
 }
 
 extern "C" void p2b_ctx_destroy(p2b_ctx* c) {
-  if (!c) return;
+  if (!c || !ctx_alive(c)) return;
+  ctx_unregister(c);
   cudaSetDevice(c->device);
   for (cudaStream_t st : {c->stream, c->stream2, c->stream_h2d, c->stream_d2h})   // all four: copies may still be in flight
     if (st) cudaStreamSynchronize(st);
@@ -614,6 +633,11 @@ struct p2b_batch {
 
 static int batch_free(p2b_batch* b) {
   if (!b) return P2B_OK;
+  if (!ctx_alive(b->ctx)) {   // the context went first: its device memory is gone with the process / pool, only the record is left
+    delete b;
+    return P2B_OK;
+  }
+  cudaSetDevice(b->ctx->device);
   cudaStream_t st = b->ctx->stream;
   if (b->coeffs) cudaFreeAsync(b->coeffs, st);
   if (b->leaves) cudaFreeAsync(b->leaves, st);
@@ -1245,6 +1269,7 @@ extern "C" int p2b_malloc(p2b_ctx* c, uint64_t bytes, void** out) {
 }
 extern "C" int p2b_free(p2b_ctx* c, void* ptr) {
   if (!c) return fail(P2B_ERR_INVALID, "NULL argument");
+  if (!ctx_alive(c)) return P2B_OK;
   CUDA_TRY(cudaSetDevice(c->device));
   CUDA_TRY(cudaFree(ptr));
   return P2B_OK;
@@ -1538,21 +1563,28 @@ extern "C" int p2b_partial_products_and_zs(p2b_ctx* c, const uint64_t* d_wires_v
   u64 *d_kis = nullptr, *d_tot = nullptr;
   auto body = [&]() -> int {
     CUDA_TRY(cudaMallocAsync(&d_kis, num_routed_wires * sizeof(u64), st));
-    CUDA_TRY(cudaMallocAsync(&d_tot, (u64)num_challenges * nb * sizeof(u64), st));
+    CUDA_TRY(cudaMallocAsync(&d_tot, ((u64)num_challenges * nb + 1) * sizeof(u64), st));
+    u32* d_flag = reinterpret_cast<u32*>(d_tot + (u64)num_challenges * nb);
+    CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(u64), st));
     CUDA_TRY(cudaMemcpyAsync(d_kis, k_is, num_routed_wires * sizeof(u64), cudaMemcpyHostToDevice, st));
     const unsigned blocks = (unsigned)((n + 127) / 128);
     const u64 w = hostf::root(degree_bits);
     if (K <= 16)
       perm::chunk_products_kernel<16><<<blocks, 128, 0, st>>>(d_wires_values, d_sigma_values, n, degree_bits, num_routed_wires,
-                                                              quotient_degree_factor, num_challenges, ch, d_kis, w, d_out);
+                                                              quotient_degree_factor, num_challenges, ch, d_kis, w, d_out, d_flag);
     else
       perm::chunk_products_kernel<64><<<blocks, 128, 0, st>>>(d_wires_values, d_sigma_values, n, degree_bits, num_routed_wires,
-                                                              quotient_degree_factor, num_challenges, ch, d_kis, w, d_out);
+                                                              quotient_degree_factor, num_challenges, ch, d_kis, w, d_out, d_flag);
     perm::block_totals_kernel<<<dim3(nb, num_challenges), perm::SCAN_BLOCK, 0, st>>>(d_out, n, nb, d_tot);
     perm::scan_totals_kernel<<<num_challenges, perm::SCAN_BLOCK, 0, st>>>(d_tot, nb);
     perm::apply_kernel<<<dim3(nb, num_challenges), perm::SCAN_BLOCK, 0, st>>>(d_out, n, nb, num_challenges, K, d_tot);
     c->launches += 4;
     CUDA_TRY(cudaGetLastError());
+    // also covers the host k_is staging above (pinned callers may reuse the buffer once this returns)
+    u32 flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, d_flag, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (flag) return fail(P2B_ERR_INVALID, "Tried to invert zero (a permutation denominator vanished; field/src/types.rs:130)");
     return P2B_OK;
   };
   int rc = body();

@@ -92,3 +92,21 @@ def test_device_chain_partial_products_commit_quotient(ctx):
     assert any(int(v) for v in vals[0])
     for b in (bz, bw, bc):
         b.close()
+
+
+def test_zero_denominator_is_an_error_like_the_reference_panic():
+    """batch_multiplicative_inverse panics with "Tried to invert zero" (field/src/types.rs:130); the device entry reports it."""
+    p2b.build()
+    ctx = p2b.Context()
+    n_log, routed = 4, 9
+    n = 1 << n_log
+    rng = np.random.default_rng(1)
+    wires = rng.integers(0, oracle.ORDER, size=(routed, n), dtype=np.uint64)
+    sigma = rng.integers(0, oracle.ORDER, size=(routed, n), dtype=np.uint64)
+    beta, gamma = 5, 11
+    # make one denominator vanish: wire + beta * sigma + gamma == 0 at (column 3, row 6)
+    wires[3, 6] = (oracle.ORDER - (beta * int(sigma[3, 6]) + gamma) % oracle.ORDER) % oracle.ORDER
+    k_is = [pow(7, j, oracle.ORDER) for j in range(routed)]
+    with pytest.raises(p2b.P2BError, match="invert zero"):
+        p2b.partial_products_and_zs(ctx, wires, sigma, k_is, [beta], [gamma], 4)
+    ctx.close()
