@@ -365,7 +365,10 @@ int p2b_field_op(p2b_ctx* ctx, int op, const uint64_t* d_a, const uint64_t* d_b,
 /* Deterministic synthetic input: out[i] = splitmix64(seed, first_index + i) rejected >= p. */
 int p2b_fill_synthetic(p2b_ctx* ctx, uint64_t* d_out, uint64_t count, uint64_t seed, uint64_t first_index);
 
-/* Device memory helpers so that non-CUDA hosts (ctypes, Rust FFI) need no second allocator. */
+/* Device memory helpers so that non-CUDA hosts (ctypes, Rust FFI) need no second allocator.  p2b_malloc / p2b_free take
+ * from / return to the device's stream-ordered pool, ordered on the context's stream (a prove() stage's buffers cost
+ * microseconds after the first proof; nothing is handed back to the driver until the process ends): use the pointer in
+ * calls on the same context, or synchronise the context before handing it to other streams. */
 int p2b_malloc(p2b_ctx* ctx, uint64_t bytes, void** out);
 int p2b_free(p2b_ctx* ctx, void* ptr);
 int p2b_malloc_host(uint64_t bytes, void** out); /* pinned */
