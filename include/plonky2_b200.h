@@ -87,6 +87,10 @@ int p2b_ctx_leaf_hash_time(p2b_ctx* ctx, double* total_ms, uint64_t* launches);
  *                     the caller supplies them so results are reproducible).  SALT_SIZE = 4, oracle.rs:41.
  * The batch keeps, on the device: coefficients [P][n]; leaves row-major [N][P + salt] in the reference's
  * bit-reversed leaf order; digests (2*(N - 2^cap_height) x 4, reference layout); cap (2^cap_height x 4).
+ * Host buffer lifetime: the calls enqueue their uploads and return without waiting for them.  Pageable host memory is
+ * staged by the runtime before the call returns; PINNED host inputs (values, coeffs, salt) are read by the copy engine
+ * later and must stay valid and unmodified until the context has been synchronised (p2b_ctx_synchronize, or any
+ * p2b_batch_get_* on the returned batch).
  * ------------------------------------------------------------------------------------------------- */
 #define P2B_SALT_SIZE 4
 
@@ -370,6 +374,9 @@ int p2b_fill_synthetic(p2b_ctx* ctx, uint64_t* d_out, uint64_t count, uint64_t s
  * microseconds after the first proof; nothing is handed back to the driver until the process ends): use the pointer in
  * calls on the same context, or synchronise the context before handing it to other streams. */
 int p2b_malloc(p2b_ctx* ctx, uint64_t bytes, void** out);
+/* How many pool allocations of this process were repeated after a transient "out of memory" from the stream-ordered
+ * allocator (diagnostics; 0 in a healthy single-device run). */
+unsigned long long p2b_debug_pool_retries(void);
 int p2b_free(p2b_ctx* ctx, void* ptr);
 int p2b_malloc_host(uint64_t bytes, void** out); /* pinned */
 int p2b_free_host(void* ptr);

@@ -138,6 +138,7 @@ def lib():
     sigs = {
         "p2b_last_error": (C.c_char_p, []),
         "p2b_version": (C.c_char_p, []),
+        "p2b_debug_pool_retries": (C.c_ulonglong, []),
         "p2b_ctx_create": (i, [i, C.POINTER(vp)]),
         "p2b_ctx_destroy": (None, [vp]),
         "p2b_ctx_stream": (vp, [vp]),

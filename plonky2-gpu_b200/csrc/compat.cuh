@@ -244,7 +244,7 @@ extern "C" p2b_rust_error fft_blinding(uint64_t* d_values_flatten, uint64_t* d_e
   const u32 log_N = (u32)(log_len + rate_bits);
   u64* rows = nullptr;
   int rc = P2B_OK;
-  if (cudaMallocAsync(&rows, N * P * sizeof(u64), c->stream) != cudaSuccess) rc = fail(P2B_ERR_OOM, "fft_blinding: scratch allocation failed");
+  if (pool_alloc(&rows, N * P * sizeof(u64), c->stream) != cudaSuccess) rc = fail(P2B_ERR_OOM, "fft_blinding: scratch allocation failed");
   if (rc == P2B_OK) rc = p2b_lde_leaves(c, d_values_flatten, (u32)log_len, P, (u32)rate_bits, rows, P, 0);
   if (rc == P2B_OK) {
     dim3 grid((unsigned)((N + 31) / 32), (unsigned)((P + 31) / 32)), block(32, 8);

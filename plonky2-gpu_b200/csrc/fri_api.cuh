@@ -64,13 +64,16 @@ static int fri_challenger_step(p2b_ctx* c, fri::Challenger* d_ch, const u64* obs
   return P2B_OK;
 }
 
-extern "C" int p2b_eval_openings(p2b_ctx* c, const p2b_batch* b, const uint64_t point[2], uint64_t* out) {
-  if (!c || !b || !point || !out) return fail(P2B_ERR_INVALID, "NULL argument");
-  if (!b->coeffs) return fail(P2B_ERR_INVALID, "batch holds no coefficients");
+// Polynomials [p0, p0 + cnt) of the batch at `point`: enqueues the two kernels on the context's stream and hands back the
+// device buffer that will hold the cnt x 2 results (eval_openings_collect copies them out and releases it).  Split in two so
+// that a multi-device caller can start every device before it waits for the first (mgpu.cuh).
+static int eval_openings_enqueue(p2b_ctx* c, const p2b_batch* b, const uint64_t point[2], u64 p0, u64 cnt, u64** d_out_ret) {
+  *d_out_ret = nullptr;
+  if (cnt == 0) return P2B_OK;
   Stage stage(c, c->stream, "construct the opening set");   // plonk/prover.rs:208-222
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
-  const u64 n = (u64)1 << b->info.degree_log, P = b->info.num_polys;
+  const u64 n = (u64)1 << b->info.degree_log;
   const u64 seg = 256 * 64;
   const u32 nblk = (u32)((n + seg - 1) / seg);
   hostf::E2h z{point[0] % gl::P, point[1] % gl::P};
@@ -78,20 +81,38 @@ extern "C" int p2b_eval_openings(p2b_ctx* c, const p2b_batch* b, const uint64_t 
   fri::E2* partial = nullptr;
   u64* d_out = nullptr;
   auto body = [&]() -> int {
-    CUDA_TRY(cudaMallocAsync(&partial, P * nblk * sizeof(fri::E2), st));
-    CUDA_TRY(cudaMallocAsync(&d_out, P * 2 * sizeof(u64), st));
-    fri::eval_partial_kernel<<<dim3(nblk, (unsigned)P), 256, 0, st>>>(b->coeffs, n, seg, fri::E2{z.a, z.b}, fri::E2{zbd.a, zbd.b}, partial);
-    fri::eval_finish_kernel<<<(unsigned)((P + 127) / 128), 128, 0, st>>>(partial, nblk, P, d_out);
+    CUDA_TRY(pool_alloc(&partial, cnt * nblk * sizeof(fri::E2), st));
+    CUDA_TRY(pool_alloc(&d_out, cnt * 2 * sizeof(u64), st));
+    fri::eval_partial_kernel<<<dim3(nblk, (unsigned)cnt), 256, 0, st>>>(b->coeffs + p0 * n, n, seg, fri::E2{z.a, z.b}, fri::E2{zbd.a, zbd.b}, partial);
+    fri::eval_finish_kernel<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(partial, nblk, cnt, d_out);
     c->launches += 2;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(out, d_out, P * 2 * sizeof(u64), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
     return P2B_OK;
   };
   int rc = body();
   if (partial) cudaFreeAsync(partial, st);
-  if (d_out) cudaFreeAsync(d_out, st);
-  return rc;
+  if (rc != P2B_OK) {
+    if (d_out) cudaFreeAsync(d_out, st);
+    return rc;
+  }
+  *d_out_ret = d_out;
+  return P2B_OK;
+}
+static int eval_openings_collect(p2b_ctx* c, u64* d_out, u64 cnt, uint64_t* out) {
+  if (!d_out) return P2B_OK;
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaError_t e = cudaMemcpyAsync(out, d_out, cnt * 2 * sizeof(u64), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFreeAsync(d_out, c->stream);
+  CUDA_TRY(e);
+  return P2B_OK;
+}
+extern "C" int p2b_eval_openings(p2b_ctx* c, const p2b_batch* b, const uint64_t point[2], uint64_t* out) {
+  if (!c || !b || !point || !out) return fail(P2B_ERR_INVALID, "NULL argument");
+  if (!b->coeffs) return fail(P2B_ERR_INVALID, "batch holds no coefficients");
+  u64* d_out = nullptr;
+  P2B_TRY(eval_openings_enqueue(c, b, point, 0, b->info.num_polys, &d_out));
+  return eval_openings_collect(c, d_out, b->info.num_polys, out);
 }
 
 // `opener` (multi-device provers, mgpu.cuh): when set, the oracles may be shards -- only their coefficient copies are read here
@@ -155,7 +176,7 @@ static int fri_prove_impl(p2b_ctx* c, const p2b_batch* const* oracles, uint32_t 
   // device state
   std::vector<void*> to_free;
   auto dalloc = [&](void** p, size_t bytes) -> int {
-    CUDA_TRY(cudaMallocAsync(p, bytes ? bytes : 8, st));
+    CUDA_TRY(pool_alloc(p, bytes ? bytes : 8, st));
     to_free.push_back(*p);
     return P2B_OK;
   };
@@ -172,7 +193,7 @@ static int fri_prove_impl(p2b_ctx* c, const p2b_batch* const* oracles, uint32_t 
 
     // ---- final polynomial (oracle.rs:1060-1084) ----
     P2B_TRY(dalloc((void**)&comp, 2 * n * sizeof(u64)));
-    CUDA_TRY(cudaMallocAsync(&fin, 2 * n * sizeof(u64), st));
+    CUDA_TRY(pool_alloc(&fin, 2 * n * sizeof(u64), st));
     pr->ctx = c;
     pr->d_final_in = fin;
     pr->final_in_len = n;
@@ -245,9 +266,9 @@ static int fri_prove_impl(p2b_ctx* c, const p2b_batch* const* oracles, uint32_t 
       t->shape = merkle::make_shape(lg_leaves, cap_height);
       t->first_leaf = 0;
       t->local_leaves = nleaves;
-      CUDA_TRY(cudaMallocAsync(&t->leaves, Ni * 2 * sizeof(u64), st));
-      CUDA_TRY(cudaMallocAsync(&t->digests, (ndig ? ndig : 1) * 4 * sizeof(u64), st));
-      CUDA_TRY(cudaMallocAsync(&t->cap, ncap * 4 * sizeof(u64), st));
+      CUDA_TRY(pool_alloc(&t->leaves, Ni * 2 * sizeof(u64), st));
+      CUDA_TRY(pool_alloc(&t->digests, (ndig ? ndig : 1) * 4 * sizeof(u64), st));
+      CUDA_TRY(pool_alloc(&t->cap, ncap * 4 * sizeof(u64), st));
       P2B_TRY(fri_ext_lde(c, coeffs, ki, rate_bits, shift, t->leaves));
       P2B_TRY(launch_hash_leaves(c, st, t->leaves, ll, 1, (u32)ll, 0, nleaves, t->shape, t->digests, t->cap));
       P2B_TRY(launch_layers(c, st, t->shape, t->digests, t->cap, 0, nleaves, 0, &t->top_layer));

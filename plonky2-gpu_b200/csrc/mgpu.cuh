@@ -574,8 +574,8 @@ extern "C" int p2b_mgpu_quotient_polys(p2b_mgpu* g, const p2b_circuit* circuit, 
     for (int d = 0; d < G; d++) {
       p2b_ctx* c = g->ctx[d];
       CUDA_TRY(cudaSetDevice(c->device));
-      CUDA_TRY(cudaMallocAsync(&parts[d], (u64)G * nc * count * sizeof(u64), c->stream));
-      CUDA_TRY(cudaMallocAsync(&vals[d], (u64)nc * lde_size * sizeof(u64), c->stream));
+      CUDA_TRY(pool_alloc(&parts[d], (u64)G * nc * count * sizeof(u64), c->stream));
+      CUDA_TRY(pool_alloc(&vals[d], (u64)nc * lde_size * sizeof(u64), c->stream));
       CUDA_TRY(cudaEventRecord(g->ev_done[d], c->stream));
     }
     for (int s = 0; s < G; s++)
@@ -645,8 +645,22 @@ extern "C" int p2b_mgpu_fri_prove_openings(p2b_mgpu* g, const p2b_mgpu_batch* co
   };
   return fri_prove_impl(g->ctx[0], first.data(), num_oracles, batches, num_batches, challenger, params, &opener, out);
 }
-// OpeningSet::new's eval_commitment (plonk/proof.rs:313-319) for one sharded batch: from the first device's coefficient copy
+// OpeningSet::new's eval_commitment (plonk/proof.rs:313-319) for one sharded batch.  Every device holds all coefficient
+// columns (they were exchanged for the LDE), so the polynomials are dealt out: device d evaluates [P d / G, P (d+1) / G) from
+// its own copy and writes its slice of `out`; all devices are started before the first result is waited for.
 extern "C" int p2b_mgpu_eval_openings(p2b_mgpu* g, const p2b_mgpu_batch* b, const uint64_t point[2], uint64_t* out) {
-  if (!g || !b || b->shard.empty()) return fail(P2B_ERR_INVALID, "NULL argument");
-  return p2b_eval_openings(g->ctx[0], b->shard[0], point, out);
+  if (!g || !b || b->shard.empty() || !point || !out) return fail(P2B_ERR_INVALID, "NULL argument");
+  const int G = g->n;
+  const u64 P = b->shard[0]->info.num_polys;
+  std::vector<u64*> d_out(G, nullptr);
+  int rc = P2B_OK;
+  for (int d = 0; d < G && rc == P2B_OK; d++) {
+    if (!b->shard[d] || !b->shard[d]->coeffs) rc = fail(P2B_ERR_INVALID, "shard %d holds no coefficients", d);
+    else rc = eval_openings_enqueue(g->ctx[d], b->shard[d], point, P * d / G, P * (d + 1) / G - P * d / G, &d_out[d]);
+  }
+  for (int d = 0; d < G; d++) {   // collect (and release) whatever was started, also after an error
+    int r2 = eval_openings_collect(g->ctx[d], d_out[d], P * (d + 1) / G - P * d / G, out + 2 * (P * d / G));
+    if (rc == P2B_OK) rc = r2;
+  }
+  return rc;
 }

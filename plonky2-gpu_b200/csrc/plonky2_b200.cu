@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <atomic>
 #include <mutex>
 #include <algorithm>
 #include <new>
@@ -52,13 +53,49 @@ static int fail(int code, const char* fmt, ...) {
   g_last_error = buf;
   return code;
 }
-#define CUDA_TRY(expr)                                                                              \
-  do {                                                                                              \
-    cudaError_t _e = (expr);                                                                        \
-    if (_e != cudaSuccess)                                                                          \
-      return fail(_e == cudaErrorMemoryAllocation ? P2B_ERR_OOM : P2B_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, \
-                  cudaGetErrorString(_e), __FILE__, __LINE__);                                      \
+// a failed allocation reports what the device had left (the figure a caller needs to size its batches)
+static int fail_cuda(cudaError_t e, const char* expr, const char* file, int line) {
+  if (e != cudaErrorMemoryAllocation) return fail(P2B_ERR_CUDA, "%s failed: %s (%s:%d)", expr, cudaGetErrorString(e), file, line);
+  int dev = -1;
+  size_t fr = 0, tot = 0;
+  cudaGetLastError();
+  cudaGetDevice(&dev);
+  cudaMemGetInfo(&fr, &tot);
+  return fail(P2B_ERR_OOM, "%s failed: %s; device %d reports %llu of %llu MiB free (%s:%d)", expr, cudaGetErrorString(e), dev,
+              (unsigned long long)(fr >> 20), (unsigned long long)(tot >> 20), file, line);
+}
+#define CUDA_TRY(expr)                                                  \
+  do {                                                                  \
+    cudaError_t _e = (expr);                                            \
+    if (_e != cudaSuccess) return fail_cuda(_e, #expr, __FILE__, __LINE__); \
   } while (0)
+// Stream-ordered allocation that survives the allocator's transient failures.  cudaMallocAsync can report "out of memory" on
+// an almost empty device: observed on 2 x B200 with peer-mapped default pools (cudaMemPoolSetAccess, mgpu.cuh) -- the pool held
+// 5984 MiB reserved / 5591 MiB used, 175 GB of the device were free, and growing the pool by 1.1 GB failed, also after a device
+// synchronisation, until the unused reserve was handed back (cudaMemPoolTrimTo).  So: retry after draining the device (blocks
+// freed on other streams become reusable), then once more after trimming the pool; a third failure is the real thing.
+static std::atomic<unsigned long long> g_pool_retries{0};
+static cudaError_t pool_alloc(void** out, size_t bytes, cudaStream_t st) {
+  cudaError_t e = cudaMallocAsync(out, bytes, st);
+  if (e != cudaErrorMemoryAllocation) return e;
+  cudaGetLastError();
+  cudaDeviceSynchronize();
+  g_pool_retries++;
+  e = cudaMallocAsync(out, bytes, st);
+  if (e != cudaErrorMemoryAllocation) return e;
+  cudaGetLastError();
+  int dev = 0;
+  cudaMemPool_t pool;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    cudaMemPoolTrimTo(pool, 0);
+    g_pool_retries++;
+    e = cudaMallocAsync(out, bytes, st);
+  }
+  return e;
+}
+template <class T>
+static cudaError_t pool_alloc(T** out, size_t bytes, cudaStream_t st) { return pool_alloc(reinterpret_cast<void**>(out), bytes, st); }
+extern "C" unsigned long long p2b_debug_pool_retries(void) { return g_pool_retries.load(); }
 #define P2B_TRY(expr)           \
   do {                          \
     int _rc = (expr);           \
@@ -739,10 +776,10 @@ static int commit_impl(p2b_ctx* c, const u64* input, int on_host, bool is_values
   u64* salt_d = nullptr;
   int rc = P2B_OK;
   auto body = [&]() -> int {
-    CUDA_TRY(cudaMallocAsync(&b->coeffs, P * n * sizeof(u64), st));
-    CUDA_TRY(cudaMallocAsync(&b->leaves, b->local_leaves * leaf_len * sizeof(u64), st));
-    CUDA_TRY(cudaMallocAsync(&b->digests, (ndig ? ndig : 1) * 4 * sizeof(u64), st));
-    CUDA_TRY(cudaMallocAsync(&b->cap, ncap * 4 * sizeof(u64), st));
+    CUDA_TRY(pool_alloc(&b->coeffs, P * n * sizeof(u64), st));
+    CUDA_TRY(pool_alloc(&b->leaves, b->local_leaves * leaf_len * sizeof(u64), st));
+    CUDA_TRY(pool_alloc(&b->digests, (ndig ? ndig : 1) * 4 * sizeof(u64), st));
+    CUDA_TRY(pool_alloc(&b->cap, ncap * 4 * sizeof(u64), st));
     P2B_TRY(ensure_scratch(c, P * n));
     const u64* in_d = input;
     bool ifft_done = false;
@@ -753,7 +790,7 @@ static int commit_impl(p2b_ctx* c, const u64* input, int on_host, bool is_values
       // Only the first group's upload is exposed (the one-shot flow waits for the whole matrix before it can hash).
       const u64 gcols = 16;
       const u64 ngroups = (P + gcols - 1) / gcols;
-      CUDA_TRY(cudaMallocAsync(&b->sponge_state, 12 * b->local_leaves * sizeof(u64), st));
+      CUDA_TRY(pool_alloc(&b->sponge_state, 12 * b->local_leaves * sizeof(u64), st));
       P2B_TRY(ensure_twiddles(c, log_N > 0 ? log_N - 1 : 0));
       CUDA_TRY(cudaEventRecord(c->ev_copy[31], st));                 // allocations above are stream-ordered on st
       CUDA_TRY(cudaStreamWaitEvent(c->stream_h2d, c->ev_copy[31], 0));
@@ -805,7 +842,7 @@ static int commit_impl(p2b_ctx* c, const u64* input, int on_host, bool is_values
     }
     if (salt) {
       if (salt_on_host) {
-        CUDA_TRY(cudaMallocAsync(&salt_d, P2B_SALT_SIZE * N * sizeof(u64), st));
+        CUDA_TRY(pool_alloc(&salt_d, P2B_SALT_SIZE * N * sizeof(u64), st));
         CUDA_TRY(cudaMemcpyAsync(salt_d, salt, P2B_SALT_SIZE * N * sizeof(u64), cudaMemcpyHostToDevice, st));
       } else {
         salt_d = const_cast<u64*>(salt);
@@ -895,11 +932,11 @@ extern "C" int p2b_commit_blocks_begin(p2b_ctx* c, uint32_t k, uint64_t P, uint3
   b->pipelined = true;
   cudaStream_t st = c->stream;
   auto body = [&]() -> int {
-    CUDA_TRY(cudaMallocAsync(&b->coeffs, P * n * sizeof(u64), st));
-    CUDA_TRY(cudaMallocAsync(&b->leaves, b->local_leaves * P * sizeof(u64), st));
-    CUDA_TRY(cudaMallocAsync(&b->digests, (ndig ? ndig : 1) * 4 * sizeof(u64), st));
-    CUDA_TRY(cudaMallocAsync(&b->cap, ncap * 4 * sizeof(u64), st));
-    CUDA_TRY(cudaMallocAsync(&b->sponge_state, 12 * b->local_leaves * sizeof(u64), st));
+    CUDA_TRY(pool_alloc(&b->coeffs, P * n * sizeof(u64), st));
+    CUDA_TRY(pool_alloc(&b->leaves, b->local_leaves * P * sizeof(u64), st));
+    CUDA_TRY(pool_alloc(&b->digests, (ndig ? ndig : 1) * 4 * sizeof(u64), st));
+    CUDA_TRY(pool_alloc(&b->cap, ncap * 4 * sizeof(u64), st));
+    CUDA_TRY(pool_alloc(&b->sponge_state, 12 * b->local_leaves * sizeof(u64), st));
     P2B_TRY(ensure_twiddles(c, log_N > 0 ? log_N - 1 : 0));
     return P2B_OK;
   };
@@ -1132,10 +1169,10 @@ static int open_impl(const p2b_batch* b, const u64* leaf_indices, u64 count, u64
   const u64 ll = b->info.leaf_len, layers = b->shape.sub_log;
   u64 *d_idx = nullptr, *d_rows = nullptr, *d_sibs = nullptr;
   auto body = [&]() -> int {
-    CUDA_TRY(cudaMallocAsync(&d_idx, count * sizeof(u64), st));
+    CUDA_TRY(pool_alloc(&d_idx, count * sizeof(u64), st));
     CUDA_TRY(cudaMemcpyAsync(d_idx, leaf_indices, count * sizeof(u64), cudaMemcpyHostToDevice, st));
-    if (rows_out) CUDA_TRY(cudaMallocAsync(&d_rows, count * ll * sizeof(u64), st));
-    if (sibs_out && layers) CUDA_TRY(cudaMallocAsync(&d_sibs, count * layers * 4 * sizeof(u64), st));
+    if (rows_out) CUDA_TRY(pool_alloc(&d_rows, count * ll * sizeof(u64), st));
+    if (sibs_out && layers) CUDA_TRY(pool_alloc(&d_sibs, count * layers * 4 * sizeof(u64), st));
     open_rows_kernel<<<(unsigned)count, 128, 0, st>>>(b->leaves - b->first_leaf * ll, ll, b->digests, b->shape, d_idx, count, d_rows, d_sibs);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1277,7 +1314,7 @@ extern "C" int p2b_malloc(p2b_ctx* c, uint64_t bytes, void** out) {
   // 100 MB, and cudaFree synchronises the device).  Every library call starts on that stream or makes its other streams
   // wait for it first, and joins them back before it returns, so stream order on it covers all uses of the buffer.
   CUDA_TRY(cudaSetDevice(c->device));
-  CUDA_TRY(cudaMallocAsync(out, bytes ? bytes : 1, c->stream));
+  CUDA_TRY(pool_alloc(out, bytes ? bytes : 1, c->stream));
   return P2B_OK;
 }
 extern "C" int p2b_free(p2b_ctx* c, void* ptr) {
@@ -1432,21 +1469,21 @@ static int quotient_impl(p2b_ctx* c, const p2b_circuit* circ, const u64* d_wires
   u64 *d_kis = nullptr, *d_alphas = nullptr, *d_apows = nullptr, *d_vals = nullptr;
   u32* d_work = nullptr;
   auto body = [&]() -> int {
-    CUDA_TRY(cudaMallocAsync(&d_gates, (gates.size() ? gates.size() : 1) * sizeof(quotient::GateDesc), st));
+    CUDA_TRY(pool_alloc(&d_gates, (gates.size() ? gates.size() : 1) * sizeof(quotient::GateDesc), st));
     if (!gates.empty()) CUDA_TRY(cudaMemcpyAsync(d_gates, gates.data(), gates.size() * sizeof(quotient::GateDesc), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMallocAsync(&d_kis, (p.num_routed ? p.num_routed : 1) * sizeof(u64), st));
+    CUDA_TRY(pool_alloc(&d_kis, (p.num_routed ? p.num_routed : 1) * sizeof(u64), st));
     if (p.num_routed) CUDA_TRY(cudaMemcpyAsync(d_kis, circ->k_is, p.num_routed * sizeof(u64), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMallocAsync(&d_alphas, nc * sizeof(u64), st));
+    CUDA_TRY(pool_alloc(&d_alphas, nc * sizeof(u64), st));
     u64 ha[quotient::MAX_CHALLENGES];
     for (u32 i = 0; i < nc; i++) ha[i] = alphas[i] % gl::P;
     CUDA_TRY(cudaMemcpyAsync(d_alphas, ha, nc * sizeof(u64), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaStreamSynchronize(st));  // host staging buffers (gates, ha) go out of scope
-    CUDA_TRY(cudaMallocAsync(&d_apows, (u64)nc * p.num_terms * sizeof(u64), st));
+    CUDA_TRY(pool_alloc(&d_apows, (u64)nc * p.num_terms * sizeof(u64), st));
     quotient::alpha_pows_kernel<<<(p.num_terms + 127) / 128, 128, 0, st>>>(d_apows, p.num_terms, nc, d_alphas);
     c->launches++;
     u64* vals = d_values_out;
     if (!vals) {
-      CUDA_TRY(cudaMallocAsync(&d_vals, nc * lde_size * sizeof(u64), st));
+      CUDA_TRY(pool_alloc(&d_vals, nc * lde_size * sizeof(u64), st));
       vals = d_vals;
     }
     p.pt_first = pt_first;
@@ -1483,7 +1520,7 @@ static int quotient_impl(p2b_ctx* c, const p2b_circuit* circ, const u64* d_wires
       std::stable_sort(items.begin(), items.end(), [](const std::pair<u64, u32>& a, const std::pair<u64, u32>& b2) { return a.first > b2.first; });
       std::vector<u32> flat;
       for (auto& it : items) flat.push_back(it.second);
-      CUDA_TRY(cudaMallocAsync(&d_work, flat.size() * sizeof(u32), st));
+      CUDA_TRY(pool_alloc(&d_work, flat.size() * sizeof(u32), st));
       CUDA_TRY(cudaMemcpyAsync(d_work, flat.data(), flat.size() * sizeof(u32), cudaMemcpyHostToDevice, st));
       CUDA_TRY(cudaStreamSynchronize(st));   // flat goes out of scope
       const u32 num_items = (u32)flat.size();
@@ -1575,8 +1612,8 @@ extern "C" int p2b_partial_products_and_zs(p2b_ctx* c, const uint64_t* d_wires_v
   }
   u64 *d_kis = nullptr, *d_tot = nullptr;
   auto body = [&]() -> int {
-    CUDA_TRY(cudaMallocAsync(&d_kis, num_routed_wires * sizeof(u64), st));
-    CUDA_TRY(cudaMallocAsync(&d_tot, ((u64)num_challenges * nb + 1) * sizeof(u64), st));
+    CUDA_TRY(pool_alloc(&d_kis, num_routed_wires * sizeof(u64), st));
+    CUDA_TRY(pool_alloc(&d_tot, ((u64)num_challenges * nb + 1) * sizeof(u64), st));
     u32* d_flag = reinterpret_cast<u32*>(d_tot + (u64)num_challenges * nb);
     CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(u64), st));
     CUDA_TRY(cudaMemcpyAsync(d_kis, k_is, num_routed_wires * sizeof(u64), cudaMemcpyHostToDevice, st));

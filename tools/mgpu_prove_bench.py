@@ -100,5 +100,5 @@ times, walls = {}, []
 for _ in range(reps):
     w, cap = prove(times)
     walls.append(w)
-print(json.dumps({"tool": "mgpu_prove_bench (single process, p2b_mgpu_*)", "n_gpus": G, "shape": "%s 2^%d x %d wires" % (kind, n_log, num_wires),
+print(json.dumps({"tool": "mgpu_prove_bench (single process, p2b_mgpu_*)", "n_gpus": G, "pool_retries": int(L.p2b_debug_pool_retries()), "shape": "%s 2^%d x %d wires" % (kind, n_log, num_wires),
                   "prove_ms": min(walls), "stages_ms": {k: min(v) for k, v in times.items()}, "wires_cap_word0": "%016x" % int(cap[0][0])}))
