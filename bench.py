@@ -45,9 +45,9 @@ FP64_PER_PERM = 5463    # DADD + DFMA
 WIDE_CYCLES, FP64_CYCLES = 4.36, 2.2
 MIXED_INT_LANES_PER_CLK_PER_SM = 119.6  # IADD3 + IMAD.X on both integer pipes (profiles/int_peak_r01.md)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE leaf-hash launch (2^20 leaves x 135) from the committed `ncu --set full`
-# capture of this bench command (profiles/r02_hash_leaves_ncu.md); a constant from that capture, not measured in this run --
+# capture of this bench command (profiles/r02c_final.md); a constant from that capture, not measured in this run --
 # the line says so in roofline.traffic_source
-HASH_LAUNCH_DRAM_BYTES_2P20_X135 = 1257786000 + 56116992
+HASH_LAUNCH_DRAM_BYTES_2P20_X135 = 1258196000 + 59403520
 INT_LANES_PER_CLK_PER_SM = 64  # measured IADD3 / IMAD issue rate on B200 (tools/int_peak.cu, profiles/int_peak_r01.md)
 
 
@@ -495,7 +495,7 @@ def run_b200(args, rank, world, local_rank):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "merkle::absorb_columns_kernel (leaf hashing, one launch per exchange round)" if pipelined else "merkle::hash_leaves_kernel", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": achieved_gbs / peaks["hbm_gbs"],
-                         "traffic": HASH_LAUNCH_DRAM_BYTES_2P20_X135 if (n_log == 20 and P == 135 and not pipelined) else None, "traffic_source": "ncu --set full capture of this command, profiles/r02_hash_leaves_ncu.md (constant, not re-measured per run)",
+                         "traffic": HASH_LAUNCH_DRAM_BYTES_2P20_X135 if (n_log == 20 and P == 135 and not pipelined) else None, "traffic_source": "ncu --set full capture of this command, profiles/r02c_final.md (constant, not re-measured per run)",
                          "peak_source": peak_kind + " (burst copy bandwidth)",
                          "launches_timed": hash_launches, "avg_launch_ms": avg_hash_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "share_of_step": hash_ms / max(dev_ms, 1e-9)},

@@ -287,12 +287,23 @@ __global__ void __launch_bounds__(512) intt_final_pass_kernel(PassArgs p, u64 n_
   u64* dst = p.dst + col * p.dst_cs;
   const int nj = (int)min((u64)J, ((u64)1 << s0) - qp0);  // s0 < log2 J: fewer chunks than J
 
-  // load: chunk j is contiguous in global memory (coalesced along l)
-  for (int i = tid; i < (J << L); i += nt) {
-    int l = i & ((1 << L) - 1), j = i >> L;
-    if (j < nj) {
-      u64 q = s0 ? (__brevll(qp0 + j) >> (64 - s0)) : 0;
-      x[l * J + j] = src[(q << L) + l];
+  // load: chunk j is contiguous in global memory (coalesced along l); eight independent loads per thread are in flight
+  // before the first one is stored (the rolled form waited on every load: long-scoreboard 4.5 per issue, profiles/r02b_ntt.md)
+  for (int i0 = tid; i0 < (J << L); i0 += 8 * nt) {
+    u64 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int i = i0 + u * nt, l = i & ((1 << L) - 1), j = i >> L;
+      v[u] = 0;
+      if (i < (J << L) && j < nj) {
+        u64 q = s0 ? (__brevll(qp0 + j) >> (64 - s0)) : 0;
+        v[u] = src[(q << L) + l];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int i = i0 + u * nt, l = i & ((1 << L) - 1), j = i >> L;
+      if (i < (J << L) && j < nj) x[l * J + j] = v[u];
     }
   }
   __syncthreads();
