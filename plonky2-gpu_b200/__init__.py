@@ -371,7 +371,8 @@ class Context:
         a, b = _np(a), _np(b)
         da, db = DeviceBuffer.from_host(self, a), DeviceBuffer.from_host(self, b)
         do = DeviceBuffer(self, a.size)
-        _check(lib().p2b_field_op(self.handle, {"add": 0, "sub": 1, "mul": 2, "mul_add": 3, "add_canonical": 4, "sub_canonical": 5}[op], da.ptr, db.ptr, do.ptr, a.size))
+        _check(lib().p2b_field_op(self.handle, {"add": 0, "sub": 1, "mul": 2, "mul_add": 3, "add_canonical": 4, "sub_canonical": 5, "add_optimistic": 6, "sub_optimistic": 7,
+                                                      "add_optimistic_flag": 8, "sub_optimistic_flag": 9}[op], da.ptr, db.ptr, do.ptr, a.size))
         return do.to_host()
 
     def poseidon(self, states):

@@ -111,10 +111,14 @@ __device__ __forceinline__ u64 mul(u64 a, u64 b) {
 struct Exact {
   static constexpr bool optimistic = false;
   bool rare = false;
+  u32 lazy_add = 0, lazy_sub = 0;   // never written in this mode (the templates below compile for both)
+  __device__ __forceinline__ bool any() const { return false; }
 };
 struct Optimistic {
   static constexpr bool optimistic = true;
   bool rare = false;
+  u32 lazy_add = 0, lazy_sub = 0;   // second wraps of the optimistic add (counted up) / sub (counted down) below
+  __device__ __forceinline__ bool any() const { return rare | ((lazy_add | lazy_sub) != 0); }
 };
 
 template <class M>
@@ -130,6 +134,30 @@ __device__ __forceinline__ u64 reduce128(u64 lo, u64 hi, M& m) {
   asm("{ sub.cc.u64 %0, %2, %3; subc.u32 %1, 0, 0; }" : "=l"(r), "=r"(w) : "l"(y), "l"((u64)h1));
   m.rare |= (w != 0) & (c == 0);
   return (u64)c * EPS + r;
+}
+// Optimistic add / sub for arbitrary u64 representatives: ONE repayment of the 64-bit wrap (2^64 == eps) instead of two.
+// The second wrap needs a + b - 2^64 >= p (both operands within 2^32 of 2^64; probability ~2^-64 on random data, but legal
+// inputs can force it), so its carry / borrow is summed into m.lazy_add / m.lazy_sub on the carry chain itself -- 7 and 6
+// SASS instructions against 10 for the exact forms; the caller redoes its work exactly when m.any().  Each chain stays of
+// one kind (add.cc -> addc, sub.cc -> subc): the carry flag read by the other kind is not what the PTX text suggests.
+template <class M>
+__device__ __forceinline__ u64 add(u64 a, u64 b, M& m) {
+  if (!M::optimistic) return add(a, b);
+  u64 s;
+  u32 c;
+  asm("{ add.cc.u64 %0, %2, %3; addc.u32 %1, 0, 0; }" : "=l"(s), "=r"(c) : "l"(a), "l"(b));
+  u64 adj = (u64)(0u - c);  // 0 or eps
+  asm("{ add.cc.u64 %0, %0, %2; addc.u32 %1, %1, 0; }" : "+l"(s), "+r"(m.lazy_add) : "l"(adj));
+  return s;
+}
+template <class M>
+__device__ __forceinline__ u64 sub(u64 a, u64 b, M& m) {
+  if (!M::optimistic) return sub(a, b);
+  u64 d;
+  u32 w;
+  asm("{ sub.cc.u64 %0, %2, %3; subc.u32 %1, 0, 0; }" : "=l"(d), "=r"(w) : "l"(a), "l"(b));  // w = -borrow: 0 or eps
+  asm("{ sub.cc.u64 %0, %0, %2; subc.u32 %1, %1, 0; }" : "+l"(d), "+r"(m.lazy_sub) : "l"((u64)w));   // counts down
+  return d;
 }
 template <class M>
 __device__ __forceinline__ u64 mul(u64 a, u64 b, M& m) {

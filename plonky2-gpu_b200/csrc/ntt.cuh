@@ -44,13 +44,13 @@ struct LevelScale {
 };
 
 // (u, v) <- (u + z v, u - z v).  M: exact or optimistic reduction (gl64.cuh); a kernel that runs the optimistic form
-// checks the CTA-wide OR of m.rare before storing and, if set (~2^-32 per butterfly), reloads its tile and redoes it
+// checks the CTA-wide OR of m.any() before storing and, if set (~2^-32 per butterfly), reloads its tile and redoes it
 // with the exact form, so results are bit-exact for every input.
 template <class M>
 __device__ __forceinline__ void butterfly(u64& u, u64& v, u64 z, M& m) {
   u64 t = gl::mul(z, v, m);
-  u64 a = gl::add(u, t);
-  v = gl::sub(u, t);
+  u64 a = gl::add(u, t, m);
+  v = gl::sub(u, t, m);
   u = a;
 }
 
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(512) ntt_strided_pass_kernel(PassArgs p, Level
   __syncthreads();
   gl::Optimistic fast;
   run_levels(x, StagedTwiddles{W}, L, T, T, tid, nt, fast);
-  if (__syncthreads_or(fast.rare | (p.force_redo != 0))) {  // the source tile is still intact (nothing stored yet): redo it exactly
+  if (__syncthreads_or(fast.any() | (p.force_redo != 0))) {  // the source tile is still intact (nothing stored yet): redo it exactly
     const u64* sp = src + (u64)l0 * stride + t;
     for (int i = tid; i < (T << L); i += nt, sp += step) x[i] = *sp;
     __syncthreads();
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(512) ntt_final_pass_kernel(PassArgs p, LevelSc
   __syncthreads();
   gl::Optimistic fast;
   run_levels(x, StagedTwiddles{W}, L, C, TP, tid, nt, fast);
-  if (__syncthreads_or(fast.rare | (p.force_redo != 0))) {
+  if (__syncthreads_or(fast.any() | (p.force_redo != 0))) {
     load_tile();
     __syncthreads();
     gl::Exact exact;

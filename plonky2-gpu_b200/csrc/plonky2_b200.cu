@@ -1268,13 +1268,25 @@ __global__ void field_op_kernel(int op, const u64* __restrict__ a, const u64* __
     case 3: r = gl::mul_add(x, y, x); break;       // x*y + x
     case 4: r = gl::add_canonical(x, gl::canon(y)); break;
     case 5: r = gl::sub_canonical(x, gl::canon(y)); break;
+    case 6: case 7: {   // the optimistic add / sub of the NTT butterflies, with the caller's duty: exact redo when flagged
+      gl::Optimistic m;
+      r = op == 6 ? gl::add(x, y, m) : gl::sub(x, y, m);
+      if (m.any()) r = op == 6 ? gl::add(x, y) : gl::sub(x, y);
+      break;
+    }
+    case 8: case 9: {   // the flag alone: 1 where the single repayment wrapped again
+      gl::Optimistic m;
+      (void)(op == 8 ? gl::add(x, y, m) : gl::sub(x, y, m));
+      out[i] = m.any() ? 1 : 0;
+      return;
+    }
     default: r = 0;
   }
   out[i] = gl::canon(r);
 }
 extern "C" int p2b_field_op(p2b_ctx* c, int op, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, uint64_t count) {
   if (!c || !d_a || !d_b || !d_out) return fail(P2B_ERR_INVALID, "NULL argument");
-  if (op < 0 || op > 5) return fail(P2B_ERR_INVALID, "unknown op %d", op);
+  if (op < 0 || op > 9) return fail(P2B_ERR_INVALID, "unknown op %d", op);
   if (count == 0) return P2B_OK;
   CUDA_TRY(cudaSetDevice(c->device));
   field_op_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(op, d_a, d_b, d_out, count);

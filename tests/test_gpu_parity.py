@@ -29,22 +29,41 @@ EDGE = np.array([0, 1, 2, P - 1, P - 2, P, P + 1, 2**64 - 1, 2**32 - 1, 2**32, 2
                  2**48, 3 * 2**48, 2**49 + 2**48, 0xFFFF * 2**48], dtype=np.uint64)
 
 
-@pytest.mark.parametrize("op", ["add", "sub", "mul", "mul_add", "add_canonical", "sub_canonical"])
+@pytest.mark.parametrize("op", ["add", "sub", "mul", "mul_add", "add_canonical", "sub_canonical", "add_optimistic", "sub_optimistic"])
 def test_field_ops_edge_and_random(ctx, op):
     rng = np.random.default_rng(11)
     a = np.concatenate([np.repeat(EDGE, EDGE.size), rng.integers(0, 2**64, size=4096, dtype=np.uint64)])
     b = np.concatenate([np.tile(EDGE, EDGE.size), rng.integers(0, 2**64, size=4096, dtype=np.uint64)])
     got = ctx.field_op(op, a, b)
     ai, bi = [int(x) for x in a], [int(x) for x in b]
-    if op in ("add", "add_canonical"):
+    if op in ("add", "add_canonical", "add_optimistic"):
         exp = [(x + y) % P for x, y in zip(ai, bi)]
-    elif op in ("sub", "sub_canonical"):
+    elif op in ("sub", "sub_canonical", "sub_optimistic"):
         exp = [(x - y) % P for x, y in zip(ai, bi)]
     elif op == "mul":
         exp = [(x * y) % P for x, y in zip(ai, bi)]
     else:
         exp = [(x * y + x) % P for x, y in zip(ai, bi)]
     assert [int(x) for x in got] == exp
+
+
+def test_optimistic_add_sub_flag_exactly_the_second_wrap(ctx):
+    """The NTT butterflies' add / sub repay the 64-bit wrap once and flag a second wrap (gl64.cuh): the flag must be set exactly
+    when a + b - 2^64 >= p (add) or a - b + 2^64 < eps with a < b (sub), so an unflagged result is always a valid representative."""
+    rng = np.random.default_rng(21)
+    top = (2**64 - 1 - rng.integers(0, 2**33, size=4096, dtype=np.uint64)).astype(np.uint64)   # operands within 2^33 of 2^64
+    low = rng.integers(0, 2**33, size=4096, dtype=np.uint64)
+    a = np.concatenate([np.repeat(EDGE, EDGE.size), top, low, top])
+    b = np.concatenate([np.tile(EDGE, EDGE.size), np.roll(top, 1), top, low])
+    ai, bi = [int(x) for x in a], [int(x) for x in b]
+    eps = 2**32 - 1
+    want_add = [1 if (x + y >= 2**64 and x + y - 2**64 + eps >= 2**64) else 0 for x, y in zip(ai, bi)]
+    want_sub = [1 if (x < y and x - y + 2**64 < eps) else 0 for x, y in zip(ai, bi)]
+    assert [int(x) for x in ctx.field_op("add_optimistic_flag", a, b)] == want_add
+    assert [int(x) for x in ctx.field_op("sub_optimistic_flag", a, b)] == want_sub
+    assert sum(want_add) > 100 and sum(want_sub) > 100      # the cases are actually exercised
+    assert [int(x) for x in ctx.field_op("add_optimistic", a, b)] == [(x + y) % P for x, y in zip(ai, bi)]
+    assert [int(x) for x in ctx.field_op("sub_optimistic", a, b)] == [(x - y) % P for x, y in zip(ai, bi)]
 
 
 def test_poseidon_reference_known_answers(ctx):
