@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/plonky2_b200.h"
