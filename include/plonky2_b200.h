@@ -190,7 +190,9 @@ int p2b_mgpu_synchronize(p2b_mgpu* g);
 int p2b_mgpu_timer_start(p2b_mgpu* g);           /* CUDA events on every device's stream ... */
 int p2b_mgpu_timer_stop_ms(p2b_mgpu* g, float* ms_max); /* ... longest span over the devices */
 /* PolynomialBatch::from_values (fri/oracle.rs:709-731): values_host [P][n] column-major (pinned memory overlaps the upload with
- * the transforms; it must stay valid until p2b_mgpu_synchronize); coeffs_host_out NULL or [P][n] (valid after the same). */
+ * the transforms; it must stay valid until p2b_mgpu_synchronize); coeffs_host_out NULL or [P][n] (valid after the same).
+ * The call enqueues the devices' work from one short-lived host thread per device (joined before it returns; environment
+ * variable P2B_MGPU_SINGLE_THREAD=1 keeps it on the caller's thread). */
 int p2b_mgpu_commit_from_values(p2b_mgpu* g, const uint64_t* values_host, uint32_t degree_log, uint64_t num_polys,
                                 uint32_t rate_bits, uint32_t cap_height, uint64_t* coeffs_host_out, p2b_mgpu_batch** out);
 /* The value matrix [P][n] sits on ONE device of the group (index src_index; e.g. Z / partial products computed there): its
