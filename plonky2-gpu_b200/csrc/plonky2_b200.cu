@@ -789,14 +789,14 @@ static int commit_impl(p2b_ctx* c, const u64* input, int on_host, bool is_values
       // H2D on the copy stream -> inverse NTT -> (coefficients back to the host on the other DMA engine) -> LDE into the
       // leaf rows -> the leaves' sponges absorb the group on stream2 while the next group uploads and transforms.
       // Only the first group's upload is exposed (the one-shot flow waits for the whole matrix before it can hash).
-      const u64 gcols = 16;
-      const u64 ngroups = (P + gcols - 1) / gcols;
+      // groups of 8, 8, 16, 16, ... columns: the first upload, the only exposed one, is half as long
+      auto group_width = [](u64 g) -> u64 { return g < 2 ? 8 : 16; };
       CUDA_TRY(pool_alloc(&b->sponge_state, 12 * b->local_leaves * sizeof(u64), st));
       P2B_TRY(ensure_twiddles(c, log_N > 0 ? log_N - 1 : 0));
       CUDA_TRY(cudaEventRecord(c->ev_copy[31], st));                 // allocations above are stream-ordered on st
       CUDA_TRY(cudaStreamWaitEvent(c->stream_h2d, c->ev_copy[31], 0));
-      for (u64 g = 0; g < ngroups; g++) {
-        const u64 c0 = g * gcols, c1 = std::min<u64>(P, c0 + gcols);
+      for (u64 g = 0, c0 = 0; c0 < P; c0 += group_width(g), g++) {
+        const u64 c1 = std::min<u64>(P, c0 + group_width(g));
         cudaEvent_t ev_up = c->ev_copy[g % 14], ev_dn = c->ev_copy[14 + g % 14];
         CUDA_TRY(cudaMemcpyAsync(b->coeffs + c0 * n, input + c0 * n, (c1 - c0) * n * sizeof(u64), cudaMemcpyHostToDevice, c->stream_h2d));
         CUDA_TRY(cudaEventRecord(ev_up, c->stream_h2d));
