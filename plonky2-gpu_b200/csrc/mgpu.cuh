@@ -397,9 +397,17 @@ static int mgpu_commit(p2b_mgpu* g, int src, const u64* values, u32 k, u64 P, u3
         rcs[s] = rc;
       };
       std::vector<std::thread> workers;
-      for (int s = 1; s < G; s++) workers.emplace_back(program, s);
-      program(0);
+      bool spawn_failed = false;
+      try {
+        workers.reserve(G - 1);
+        for (int s = 1; s < G; s++) workers.emplace_back(program, s);
+      } catch (...) {   // no exception crosses the C ABI: the threads already running are told to stop and joined
+        spawn_failed = true;
+        abort_flag.store(1, std::memory_order_relaxed);
+      }
+      if (!spawn_failed) program(0);
       for (auto& w : workers) w.join();
+      if (spawn_failed) return fail(P2B_ERR_CUDA, "multi-device commit: could not start the per-device issue threads (set P2B_MGPU_SINGLE_THREAD=1)");
       for (int s = 0; s < G; s++)
         if (rcs[s] != P2B_OK) {
           g_last_error = errs[s];
